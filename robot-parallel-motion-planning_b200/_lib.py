@@ -1,0 +1,71 @@
+"""ctypes binding of libgmt_b200.so -- one prototype per entry point of include/gmt_c_api.h."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgmt_b200.so")
+
+GMT_OK = 0
+GMT_STATUS_GOAL = 0
+GMT_STATUS_LIMIT = 1
+
+
+class GmtResult(C.Structure):
+    """struct gmt_result (include/gmt_c_api.h)."""
+    _fields_ = [("status", C.c_int), ("iterations", C.c_int), ("goal_cost", C.c_float),
+                ("route_len", C.c_int), ("device_ms", C.c_float), ("grid_overflow", C.c_int),
+                ("edge_pairs", C.c_longlong), ("edge_evals", C.c_longlong),
+                ("word_checks", C.c_longlong), ("launches", C.c_int), ("reserved", C.c_int)]
+
+
+class GmtError(RuntimeError):
+    pass
+
+
+# every symbol include/gmt_c_api.h declares: name -> (restype, argtypes)
+_vp, _i, _f, _ip, _fp = C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_float)
+PROTOTYPES = {
+    "gmt_create": (_i, [_vp, _i, _vp, _vp, _i, C.POINTER(_vp)]),
+    "gmt_destroy": (_i, [_vp]),
+    "gmt_set_stream": (_i, [_vp, _vp]),
+    "gmt_plan": (_i, [_vp, _i, _i, _f, _f, _vp, _i, _i, C.POINTER(GmtResult)]),
+    "gmt_set_obstacles": (_i, [_vp, _vp, _i]),
+    "gmt_plan_resident": (_i, [_vp, _i, _i, _f, _f, _i, C.POINTER(GmtResult)]),
+    "gmt_get_route": (_i, [_vp, _vp, _i, _ip]),
+    "gmt_get_parent": (_i, [_vp, _vp]),
+    "gmt_get_cost": (_i, [_vp, _vp]),
+    "gmt_set_trace": (_i, [_vp, _i]),
+    "gmt_get_trace": (_i, [_vp, _vp, _i, _vp, C.c_longlong, C.POINTER(C.c_longlong), _vp]),
+    "gmt_edge_costs": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _fp]),
+    "gmt_sample_states": (_i, [C.c_uint, _i, _f, _i, _i, _vp]),
+    "gmt_build_neighbors": (_i, [_vp, _i, C.c_double, _i, C.POINTER(_vp), C.POINTER(_vp),
+                                 C.POINTER(C.c_longlong)]),
+    "gmt_free": (None, [_vp]),
+    "gmt_plan_batch": (_i, [_vp, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _i]),
+    "gmt_last_error": (C.c_char_p, []),
+    "gmt_version": (_i, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; there is deliberately no fallback when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GmtError("%s is missing -- build it with `python %s` (nvcc, sm_100a); this planner "
+                           "has no CPU fallback" % (LIB_PATH, os.path.join(HERE, "build.py")))
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != GMT_OK:
+        msg = load().gmt_last_error()
+        raise GmtError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))

@@ -1,0 +1,193 @@
+"""gmt_planner.py -- drop-in for the reference module of the same name.
+
+The reference's callers do ``from gmt_planner import *`` and use the name ``GMT`` only
+(/root/reference/carla/cuda_agent.py:11,122,218; carla/test_agent.py:30,141,232).  This module
+keeps that surface -- ``GMT(init_parameters, debug=False)`` and
+``run_step(iter_parameters, iter_limit=1000, debug=False, time=False) -> route`` with the same
+dict keys, the same goal-first route list, the same stale-route behaviour on failure and the
+same public attributes (``route, start, goal, n, parent, time_data`` ...) as
+/root/reference/carla/gmt_planner.py:22-239 -- while the planning itself is one persistent
+CUDA kernel for sm_100a behind the C ABI of include/gmt_c_api.h (ctypes, no PyCuda, no CPU
+fallback: importing this module without the built library raises).
+"""
+import ctypes as C
+
+import numpy as np
+
+try:
+    from . import _lib
+except ImportError:  # imported as a top-level module, the way the reference's callers do
+    import _lib
+
+__all__ = ["GMT"]
+
+
+class GMT(object):
+    """GMT* planner over a fixed Dubins roadmap (reference: carla/gmt_planner.py:22-239)."""
+
+    # the reference prints its exit reason (gmt_planner.py:144,151); set True to get the same lines
+    verbose = False
+
+    def __init__(self, init_parameters, debug=False, device=0):
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        self._cpu_init(init_parameters, debug)
+        self._gpu_init(debug, device)
+
+        self.route = []
+        self.start = 0
+        self.time_data = {"wavefront": [], "wavefront_compact": [], "open_compact": [], "neighbors": [],
+                          "neighbors_compact": [], "connection": [], "elapsed": [], "threshold": [],
+                          "goal": [], "iteration": []}
+        self.last_result = None
+
+    # ---- gmt_planner.py:31-44 ---------------------------------------------------------------
+    def _cpu_init(self, init_parameters, debug):
+        self.states = init_parameters['states']
+        self.n = self.states.shape[0]
+        self.waypoints = np.arange(self.n).astype(np.int32)
+        self.neighbors = init_parameters['neighbors']
+        self.num_neighbors = init_parameters['num_neighbors']
+        # kept for callers that poke at them; the device owns the live copies
+        self.cost = np.full(self.n, np.inf).astype(np.float32)
+        self.Vunexplored = np.full(self.n, 1).astype(np.int32)
+        self.Vopen = np.zeros_like(self.Vunexplored).astype(np.int32)
+        self.threadsPerBlock = init_parameters.get('threadsPerBlock', 128)  # accepted, not needed
+        if debug:
+            print('neighbors: ', self.neighbors)
+            print('number neighbors: ', self.num_neighbors)
+
+    # ---- gmt_planner.py:50-61: roadmap to the device, once ---------------------------------------
+    def _gpu_init(self, debug, device=0):
+        states = np.ascontiguousarray(self.states, dtype=np.float32).reshape(self.n, 3)
+        nbr = np.ascontiguousarray(self.neighbors, dtype=np.int32).reshape(-1)
+        cnt = np.ascontiguousarray(self.num_neighbors, dtype=np.int32).reshape(-1)
+        if cnt.shape[0] != self.n:
+            raise ValueError("num_neighbors must have one entry per state")
+        if int(cnt.sum()) != nbr.shape[0]:
+            raise ValueError("neighbors does not hold sum(num_neighbors) entries")
+        rc = self._lib.gmt_create(states.ctypes.data, self.n, nbr.ctypes.data if nbr.size else None,
+                                  cnt.ctypes.data, int(device), C.byref(self._handle))
+        _lib.check(rc, "gmt_create")
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                self._lib.gmt_destroy(h)
+            except Exception:
+                pass
+            self._handle = C.c_void_p()
+
+    # ---- gmt_planner.py:63-101 -------------------------------------------------------------------
+    def step_init(self, iter_parameters, debug):
+        if self.start != iter_parameters['start'] and len(self.route) > 2:
+            del self.route[-1]                                 # gmt_planner.py:68-69
+
+        self.obstacles = iter_parameters['obstacles']
+        self.num_obs = iter_parameters['num_obs']
+        self.start = iter_parameters['start']
+        self.goal = iter_parameters['goal']
+        self.radius = iter_parameters['radius']
+        self.threshold = np.array([iter_parameters['threshold']]).astype(np.float32)
+        self._parent = None
+        self._cost = None
+
+    def get_path(self):
+        """gmt_planner.py:103-107 -- the walk goal -> start happened on the device."""
+        cap = self.n + 1
+        buf = np.zeros(cap, np.int32)
+        ln = C.c_int()
+        _lib.check(self._lib.gmt_get_route(self._handle, buf.ctypes.data, cap, C.byref(ln)), "gmt_get_route")
+        self.route += [int(v) for v in buf[:ln.value]]
+
+    # ---- results the reference downloads (gmt_planner.py:145,152) plus the cost array -----------
+    @property
+    def parent(self):
+        if getattr(self, "_parent", None) is None:
+            out = np.zeros(self.n, np.int32)
+            _lib.check(self._lib.gmt_get_parent(self._handle, out.ctypes.data), "gmt_get_parent")
+            self._parent = out
+        return self._parent
+
+    @parent.setter
+    def parent(self, value):
+        self._parent = value
+
+    @property
+    def dev_cost(self):
+        """cost[] after the last plan (the reference never downloads it; parity tests need it)."""
+        if getattr(self, "_cost", None) is None:
+            out = np.zeros(self.n, np.float32)
+            _lib.check(self._lib.gmt_get_cost(self._handle, out.ctypes.data), "gmt_get_cost")
+            self._cost = out
+        return self._cost
+
+    # ---- gmt_planner.py:109-239 ------------------------------------------------------------------
+    def run_step(self, iter_parameters, iter_limit=1000, debug=False, time=False):
+        self.step_init(iter_parameters, debug)
+        num_obs = int(np.asarray(self.num_obs).reshape(-1)[0])
+        obs = np.ascontiguousarray(self.obstacles, dtype=np.float32).reshape(-1, 4)
+        if num_obs > obs.shape[0]:
+            raise ValueError("num_obs exceeds the obstacle array")
+        want_trace = bool(debug or time)
+        _lib.check(self._lib.gmt_set_trace(self._handle, 1 if want_trace else 0), "gmt_set_trace")
+        res = _lib.GmtResult()
+        rc = self._lib.gmt_plan(self._handle, int(self.start), int(self.goal),
+                                float(np.float32(self.radius)), float(self.threshold[0]),
+                                obs.ctypes.data if num_obs > 0 else None, num_obs, int(iter_limit),
+                                C.byref(res))
+        _lib.check(rc, "gmt_plan")
+        self.last_result = res
+        self.iterations = res.iterations
+        self.status = res.status
+
+        if res.status == _lib.GMT_STATUS_LIMIT:
+            if self.verbose:
+                print('### iteration limit ###', res.iterations)
+            if res.route_len >= 0:                             # parent[goal] != -1, gmt_planner.py:146
+                self.route = []
+                self.get_path()
+        else:
+            if self.verbose:
+                print('### goal reached ### ', res.iterations)
+            self.route = []
+            self.get_path()
+
+        if want_trace:
+            self._collect_trace(res.iterations, debug, time)
+        return self.route
+
+    def _collect_trace(self, iterations, debug, time):
+        sizes = np.zeros((max(iterations, 1), 3), np.int32)
+        ms = np.zeros(max(iterations, 1), np.float32)
+        cap = 4 * self.n + 1024
+        sets = np.zeros(cap, np.int32)
+        ln = C.c_longlong()
+        _lib.check(self._lib.gmt_get_trace(self._handle, sizes.ctypes.data, iterations, sets.ctypes.data,
+                                           cap, C.byref(ln), ms.ctypes.data), "gmt_get_trace")
+        self.trace = []
+        pos = 0
+        for k in range(iterations):
+            g, y, x = (int(v) for v in sizes[k])
+            ent = {"gSize": g, "ySize": y, "xSize": x}
+            ent["G"] = sets[pos:pos + g].copy(); pos += g
+            if y > 0:
+                ent["Y"] = sets[pos:pos + y].copy(); pos += y
+            if x > 0:
+                ent["X"] = sets[pos:pos + x].copy(); pos += x
+            self.trace.append(ent)
+            if debug:
+                print('y size: ', y, 'G size: ', g, 'x size: ', x)
+                print(f'######### iteration: {k + 1} iteration time: {ms[k] * 1e-3}')
+            # the reference only times turns that reach the end of the loop body (gmt_planner.py:229)
+            if time and y > 0 and x > 0:
+                # per-phase host timers of the reference have no counterpart inside one persistent
+                # kernel: the device time of the turn is reported as elapsed/connection, rest 0
+                sec = float(ms[k]) * 1e-3
+                for key in ("wavefront", "wavefront_compact", "open_compact", "neighbors",
+                            "neighbors_compact", "threshold", "goal"):
+                    self.time_data[key].append(0.0)
+                self.time_data["connection"].append(sec)
+                self.time_data["elapsed"].append(sec)
+                self.time_data["iteration"].append(k + 1)

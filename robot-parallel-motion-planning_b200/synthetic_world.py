@@ -1,0 +1,143 @@
+"""synthetic_world.py -- the 2-D world that stands in for CARLA (host side, NumPy).
+
+Produces exactly the two dicts the planner consumes (reference: carla/cuda_agent.py:115,215):
+``init_parameters`` {'states','neighbors','num_neighbors','threadsPerBlock'} and
+``iter_parameters`` {'start','goal','radius','threshold','obstacles','num_obs'}.
+
+World definition: square of side
+S = sqrt(n / 0.55) m, neighbour radius 4*sqrt(2) m (cuda_agent.py:56), AABB obstacles with
+half-extents U[1,5] m given as two opposite corners (cuda_agent.py:196-206), start / goal = the
+states nearest (0.1 S, 0.1 S) / (0.9 S, 0.9 S), radius 2.0, threshold 1.0
+(test_agent.py:199-200).  States come from ``sampler(seed, n, side, mode)`` and the CSR lists
+from ``neighbor_builder(states, radius)``: by default the CUDA builders of the library
+(gmt_sample_states / gmt_build_neighbors); CPU-only tests pass the NumPy restatements of
+oracle/world_oracle.py instead.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+try:
+    from . import _lib
+except ImportError:
+    import _lib
+
+DENSITY = 0.55
+DISK_RADIUS = 4 * math.sqrt(2)
+
+# BASELINE.json configs 1..5
+CONFIGS = {
+    1: dict(n=2000, m=20, mode="uniform", layout="uniform"),
+    2: dict(n=10000, m=100, mode="uniform", layout="uniform"),
+    3: dict(n=100000, m=2000, mode="uniform", layout="roads"),
+    4: dict(n=10000, m=100, mode="uniform", layout="uniform", queries=4096),
+    5: dict(n=1000000, m=2000, mode="uniform", layout="uniform"),
+}
+
+
+def cuda_sampler(seed, n, side, mode="uniform", device=0):
+    """gmt_sample_states: Philox4x32-10 sampler on the device."""
+    lib = _lib.load()
+    out = np.zeros((int(n), 3), np.float32)
+    rc = lib.gmt_sample_states(int(seed) & 0xFFFFFFFF, int(n), float(np.float32(side)),
+                               0 if mode == "uniform" else 1, int(device), out.ctypes.data)
+    _lib.check(rc, "gmt_sample_states")
+    return out
+
+
+def cuda_neighbor_builder(states, disk_radius=DISK_RADIUS, device=0):
+    """gmt_build_neighbors: cell-grid radius search on the device -> (neighbors, num_neighbors)."""
+    lib = _lib.load()
+    states = np.ascontiguousarray(states, np.float32)
+    n = states.shape[0]
+    vals, counts, total = C.c_void_p(), C.c_void_p(), C.c_longlong()
+    rc = lib.gmt_build_neighbors(states.ctypes.data, n, float(disk_radius), int(device),
+                                 C.byref(vals), C.byref(counts), C.byref(total))
+    _lib.check(rc, "gmt_build_neighbors")
+    try:
+        num = np.ctypeslib.as_array(C.cast(counts, C.POINTER(C.c_int)), shape=(n,)).copy()
+        nbr = (np.ctypeslib.as_array(C.cast(vals, C.POINTER(C.c_int)), shape=(max(total.value, 1),))
+               [:total.value].copy())
+    finally:
+        lib.gmt_free(vals)
+        lib.gmt_free(counts)
+    return nbr.astype(np.int32), num.astype(np.int32)
+
+
+def world_side(n):
+    return math.sqrt(n / DENSITY)
+
+
+def make_obstacles(rng, m, side, layout, keep_out):
+    """m AABBs [xa, ya, xb, yb]; rejected while they contain one of the keep_out points."""
+    boxes = []
+    keep_out = np.asarray(keep_out, np.float64).reshape(-1, 2)
+    while len(boxes) < m:
+        c = rng.uniform(0.0, side, 2)
+        if layout == "roads":
+            # streets every 40 m, 12 m wide: keep centres on a street
+            on_street = (abs((c[0] + 20.0) % 40.0 - 20.0) < 6.0) or (abs((c[1] + 20.0) % 40.0 - 20.0) < 6.0)
+            if not on_street:
+                continue
+        h = rng.uniform(1.0, 5.0, 2)
+        lo, hi = c - h, c + h
+        inside = np.all((keep_out >= lo - 0.5) & (keep_out <= hi + 0.5), axis=1)
+        if inside.any():
+            continue
+        # the reference stores two opposite corners in arbitrary order (cuda_agent.py:197)
+        if rng.random() < 0.5:
+            boxes.append([hi[0], hi[1], lo[0], lo[1]])
+        else:
+            boxes.append([lo[0], lo[1], hi[0], hi[1]])
+    if m == 0:
+        return np.array([[-1, -1, -1, -1]]).astype(np.float32), np.array([0]).astype(np.int32)
+    return np.array(boxes).astype(np.float32), np.array([m]).astype(np.int32)
+
+
+def nearest_state(states, x, y):
+    d = (states[:, 0].astype(np.float64) - x) ** 2 + (states[:, 1].astype(np.float64) - y) ** 2
+    return int(np.argmin(d))
+
+
+def make_world(config=None, n=None, m=None, mode=None, layout=None, seed=None, sampler=None,
+               neighbor_builder=None, radius=2.0, threshold=1.0, side=None):
+    """Returns (init_parameters, iter_parameters, meta) for a BASELINE config or explicit sizes."""
+    cfg = dict(CONFIGS[config]) if config is not None else {}
+    n = int(n if n is not None else cfg["n"])
+    m = int(m if m is not None else cfg["m"])
+    mode = mode or cfg.get("mode", "uniform")
+    layout = layout or cfg.get("layout", "uniform")
+    seed = int(seed if seed is not None else 18 + (config or 0))       # seed base 18, run.py:45
+    sampler = sampler or cuda_sampler
+    neighbor_builder = neighbor_builder or cuda_neighbor_builder
+    side = float(side if side is not None else world_side(n))
+
+    states = np.ascontiguousarray(sampler(seed, n, side, mode), np.float32)
+    n = states.shape[0]
+    neighbors, num_neighbors = neighbor_builder(states, DISK_RADIUS)
+    start = nearest_state(states, 0.1 * side, 0.1 * side)
+    goal = nearest_state(states, 0.9 * side, 0.9 * side)
+    rng = np.random.default_rng(seed)
+    obstacles, num_obs = make_obstacles(rng, m, side, layout, [states[start, :2], states[goal, :2]])
+
+    init_parameters = {'states': states, 'neighbors': neighbors, 'num_neighbors': num_neighbors,
+                       'threadsPerBlock': 128}
+    iter_parameters = {'start': start, 'goal': goal, 'radius': radius, 'threshold': threshold,
+                       'obstacles': obstacles, 'num_obs': num_obs}
+    meta = dict(n=n, m=m, side=side, seed=seed, mode=mode, layout=layout,
+                mean_degree=float(num_neighbors.mean()) if n else 0.0)
+    return init_parameters, iter_parameters, meta
+
+
+def make_queries(states, side, q, seed):
+    """q (start, goal) pairs drawn uniformly with |start - goal| >= side/2 (BASELINE config 4)."""
+    rng = np.random.default_rng(seed)
+    n = states.shape[0]
+    starts, goals = [], []
+    while len(starts) < q:
+        a, b = int(rng.integers(0, n)), int(rng.integers(0, n))
+        if np.hypot(*(states[a, :2] - states[b, :2])) >= side / 2:
+            starts.append(a)
+            goals.append(b)
+    return np.array(starts, np.int32), np.array(goals, np.int32)
