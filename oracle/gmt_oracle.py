@@ -122,8 +122,10 @@ class OraclePort:
         out = dict(status=status, iterations=iters.value, cost=cost, parent=parent, open=opn,
                    unexplored=unexp)
         route = np.zeros(n + 1, np.int32)
-        ln = self.lib.gmto_get_path(parent, n, int(goal), route, n + 1)
-        out["route"] = [int(v) for v in route[:ln]] if parent[int(goal)] != -1 or status == 0 else []
+        out["route"] = []
+        if int(goal) >= 0 and (parent[int(goal)] != -1 or status == 0):
+            ln = self.lib.gmto_get_path(parent, n, int(goal), route, n + 1)
+            out["route"] = [int(v) for v in route[:ln]]
         if trace:
             out["trace"] = _split_trace(sizes[:iters.value], sets[:sets_len.value])
         return out
@@ -301,14 +303,22 @@ class OracleGMT(object):
             self.route.append(int(p))
             p = self.parent[p]
 
-    def run_step(self, iter_parameters, iter_limit=1000, debug=False, time=False):
-        # gmt_planner.py:109-204
+    def run_step(self, iter_parameters, iter_limit=1000, debug=False, time=False, budget_s=None):
+        # gmt_planner.py:109-204.  budget_s (bench only): stop after that many seconds of
+        # dubinConnection work with status 2 -- a bounded SAMPLE of the plan, not a plan.
+        import time as _time
         b, n, tpb = self.backend, self.n, self.threadsPerBlock
         self.step_init(iter_parameters)
         self.trace = []
         self.status = None
+        self.edge_pairs = 0
+        self.connect_seconds = 0.0
         iteration = 0
         while True:
+            if budget_s is not None and self.connect_seconds > budget_s:
+                self.status = 2
+                self.iterations = iteration
+                return self.route
             iteration += 1
             b.k_wavefront(self.dev_Gindicator, self.dev_open, self.dev_cost, self.dev_threshold, n, tpb)
             b.k_grow_threshold(self.dev_threshold, self.dev_radius)
@@ -352,6 +362,9 @@ class OracleGMT(object):
             dev_x = np.zeros(xSize, np.int32)
             b.k_compact(dev_x, dev_xscan, dev_xindicator, self.waypoints, n, tpb)
             ent["X"] = dev_x.copy()
+            t0 = _time.perf_counter()
             b.k_dubin_connection(self.dev_cost, self.dev_parent, dev_x, dev_y, self.states, self.dev_open,
                                  self.dev_unexplored, xSize, ySize, self.obstacles, self.num_obs,
                                  self.dev_radius, tpb)
+            self.connect_seconds += _time.perf_counter() - t0
+            self.edge_pairs += xSize * ySize

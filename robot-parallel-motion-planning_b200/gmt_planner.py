@@ -161,9 +161,10 @@ class GMT(object):
     def _collect_trace(self, iterations, debug, time):
         sizes = np.zeros((max(iterations, 1), 3), np.int32)
         ms = np.zeros(max(iterations, 1), np.float32)
-        cap = 4 * self.n + 1024
-        sets = np.zeros(cap, np.int32)
         ln = C.c_longlong()
+        _lib.check(self._lib.gmt_get_trace(self._handle, None, 0, None, 0, C.byref(ln), None), "gmt_get_trace")
+        cap = max(int(ln.value), 1)
+        sets = np.zeros(cap, np.int32)
         _lib.check(self._lib.gmt_get_trace(self._handle, sizes.ctypes.data, iterations, sets.ctypes.data,
                                            cap, C.byref(ln), ms.ctypes.data), "gmt_get_trace")
         self.trace = []

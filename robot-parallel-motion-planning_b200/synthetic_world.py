@@ -130,6 +130,31 @@ def make_world(config=None, n=None, m=None, mode=None, layout=None, seed=None, s
     return init_parameters, iter_parameters, meta
 
 
+def explore_cuda(init_parameters, iter_parameters, iter_limit=1000, device=0):
+    """Runs the planner without a goal and returns the ids that ever entered a wavefront G."""
+    try:
+        from .gmt_planner import GMT
+    except ImportError:
+        from gmt_planner import GMT
+    g = GMT(init_parameters, device=device)
+    g.run_step(dict(iter_parameters, goal=-1), iter_limit=iter_limit, debug=False, time=True)
+    members = [e["G"] for e in g.trace if e["gSize"] > 0]
+    return np.unique(np.concatenate(members)) if members else np.zeros(0, np.int32)
+
+
+def pick_reachable_goal(init_parameters, iter_parameters, side, explore=None, frac=0.9):
+    """The reference's GMT variant closes every open node above the cost threshold unexpanded
+    (kernel.py:445), so on a random roadmap many states can never enter a
+    wavefront and a plan to them spins to iter_limit.  Benchmark queries therefore use as goal the
+    state nearest (frac*S, frac*S) among those that DO enter a wavefront from this start."""
+    reach = (explore or explore_cuda)(init_parameters, iter_parameters)
+    states = init_parameters['states']
+    if len(reach) == 0:
+        return int(iter_parameters['goal'])
+    d = (states[reach, 0].astype(np.float64) - frac * side) ** 2 + (states[reach, 1].astype(np.float64) - frac * side) ** 2
+    return int(reach[int(np.argmin(d))])
+
+
 def make_queries(states, side, q, seed):
     """q (start, goal) pairs drawn uniformly with |start - goal| >= side/2 (BASELINE config 4)."""
     rng = np.random.default_rng(seed)

@@ -1,0 +1,370 @@
+"""GPU: the CUDA path (through the C ABI / the GMT drop-in class) against the oracles.
+
+Bars (BASELINE.json north_star): bit-exact neighbour sets, collision verdicts, frontier / open /
+candidate membership per wavefront and tree parents; path cost within 1e-5 relative.  Checked
+  * against the committed golden vectors (reference source compiled for the host),
+  * against oracle/gmt_oracle.c in its libdevice-emulating flavour on seeded worlds,
+  * against the reference's own kernels on this GPU (oracle/_ref/ref_kernel.cubin) bit for bit,
+    costs included, when that cubin travelled here,
+  * and at BASELINE.json's full sizes through size-independent properties.
+Nothing here reads /root/reference.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.fixtures import FIXTURES
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+UNIT = json.load(open(os.path.join(GOLD, "unit_tests.json")))
+RTOL = 1e-5          # north_star: path cost within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def GMT(gmt_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from gmt_planner import GMT as cls
+    return cls
+
+
+@pytest.fixture(scope="module")
+def refgpu():
+    from oracle.ref_gpu import RefGpu
+    if not RefGpu.available():
+        pytest.skip("oracle/_ref/ref_kernel.cubin did not travel to this box")
+    return RefGpu()
+
+
+def report(line):
+    """Parity statistics worth keeping (copied into profiles/ by hand): gpurun_out/parity_report.txt."""
+    print(line)
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_report.txt"), "a") as f:
+            f.write(line + "\n")
+
+
+def _world(oracles_unused, n, m, seed, mode="uniform", layout="uniform", reachable=True):
+    """Synthetic world from the CUDA builders; the goal is the reachable state nearest the far corner
+    (synthetic_world.pick_reachable_goal) so that plans end with "goal reached"."""
+    import synthetic_world as sw
+    init, it, meta = sw.make_world(n=n, m=m, seed=seed, mode=mode, layout=layout)
+    if reachable:
+        it = dict(it, goal=sw.pick_reachable_goal(init, it, meta["side"]))
+    return init, it, meta
+
+
+def _edge(gmt_lib, states, nbr, num, obstacles, m, y, x, radius):
+    h = C.c_void_p()
+    states = np.ascontiguousarray(states, np.float32)
+    nbr = np.ascontiguousarray(nbr, np.int32)
+    num = np.ascontiguousarray(num, np.int32)
+    import _lib
+    _lib.check(gmt_lib.gmt_create(states.ctypes.data, states.shape[0], nbr.ctypes.data if nbr.size else None,
+                                  num.ctypes.data, 0, C.byref(h)), "gmt_create")
+    try:
+        obs = np.ascontiguousarray(obstacles, np.float32)
+        _lib.check(gmt_lib.gmt_set_obstacles(h, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
+        P = len(y)
+        cost4 = np.zeros((P, 4), np.float32)
+        bits = np.zeros(P, np.uint32)
+        best = np.zeros(P, np.float32)
+        ms = C.c_float()
+        y = np.ascontiguousarray(y, np.int32)
+        x = np.ascontiguousarray(x, np.int32)
+        _lib.check(gmt_lib.gmt_edge_costs(h, y.ctypes.data, x.ctypes.data, P, float(radius), cost4.ctypes.data,
+                                          bits.ctypes.data, best.ctypes.data, C.byref(ms)), "gmt_edge_costs")
+    finally:
+        gmt_lib.gmt_destroy(h)
+    return cost4, bits, best
+
+
+def _ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures of the reference (carla/pycuda_example.py:854-956)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_unit_fixtures_match_reference_golden(GMT, name):
+    init, it = FIXTURES[name]()
+    gold = UNIT[name]
+    g = GMT(init)
+    route = g.run_step(it, iter_limit=20, debug=True)
+    assert (g.status, g.iterations) == (gold["status"], gold["iterations"])
+    assert route == gold["route"]
+    assert g.parent.tolist() == gold["parent"]
+    gc = np.array(gold["cost_bits"], np.uint32).view(np.float32)
+    assert np.array_equal(np.isfinite(g.dev_cost), np.isfinite(gc))
+    fin = np.isfinite(gc)
+    np.testing.assert_allclose(g.dev_cost[fin], gc[fin], rtol=RTOL)
+    assert len(g.trace) == len(gold["trace"])
+    for a, b in zip(g.trace, gold["trace"]):
+        assert (a["gSize"], a["ySize"], a["xSize"]) == (b["gSize"], b["ySize"], b["xSize"])
+        for key in ("G", "Y", "X"):
+            if key in b:
+                assert np.asarray(a[key]).tolist() == b[key], (name, key)
+
+
+@pytest.mark.parametrize("tag", ["r1", "r2"])
+def test_edge_kernel_matches_golden_and_oracle(gmt_lib, oracles, tag):
+    e = np.load(os.path.join(GOLD, "edge_vectors_%s.npz" % tag))
+    states, obs, y, x, radius = e["states"], e["obstacles"], e["y"], e["x"], float(e["radius"])
+    n, m = states.shape[0], obs.shape[0]
+    cost4, bits, best = _edge(gmt_lib, states, np.zeros(0, np.int32), np.zeros(n, np.int32), obs, m, y, x, radius)
+    o4, obits, obest = oracles["cuda"].edge_costs(states, y, x, radius, obs, [m])
+    # against the libdevice-emulating oracle: structure identical, costs identical up to the one
+    # hardware-defined instruction of powf (rcp.approx), i.e. a few ulp on a small fraction
+    assert np.array_equal(np.isnan(cost4), np.isnan(o4))
+    ok = ~np.isnan(o4)
+    ulp = _ulp_diff(cost4[ok], o4[ok])
+    report("edge %s: cost words differing from cuda-flavour oracle: %d of %d (max %d ulp); verdict words differing: %d"
+          % (tag, int((ulp > 0).sum()), int(ok.sum()), int(ulp.max()), int((bits != obits).sum())))
+    assert np.mean(ulp > 4) < 2e-3
+    assert np.mean(bits != obits) < 2e-3                # boundary cases only (logged above)
+    # against the reference-source golden (glibc math): 1e-5 relative except wrap flips
+    gold = e["cost4_bits"].view(np.float32)
+    assert np.array_equal(np.isnan(cost4), np.isnan(gold))
+    rel = np.abs(cost4[ok] - gold[ok]) / np.maximum(np.abs(gold[ok]), 1e-3)
+    assert np.mean(rel > RTOL) < 2e-3
+    assert np.mean(bits != e["verdict_bits"]) < 5e-3
+
+
+def test_edge_kernel_bit_exact_vs_reference_cubin(gmt_lib, refgpu):
+    """Same GPU, same libdevice: word lengths, verdicts and minima must be IDENTICAL bit patterns."""
+    rng = np.random.default_rng(3)
+    for side, n, m, radius in ((40.0, 800, 14, 2.0), (1400.0, 1500, 120, 2.9), (25.0, 300, 0, 1.0)):
+        states = np.stack([rng.uniform(0, side, n), rng.uniform(0, side, n), rng.uniform(-np.pi, np.pi, n)],
+                          1).astype(np.float32)
+        c = rng.uniform(0, side, (max(m, 1), 2))
+        hh = rng.uniform(0.5, 3.0, (max(m, 1), 2))
+        obs = np.concatenate([c + hh, c - hh], 1).astype(np.float32)
+        y = rng.integers(0, n, 20000).astype(np.int32)
+        x = ((y + 1 + rng.integers(0, n - 1, 20000)) % n).astype(np.int32)
+        a4, abits, abest = _edge(gmt_lib, states, np.zeros(0, np.int32), np.zeros(n, np.int32), obs, m, y, x, radius)
+        r4, rbits, rbest = refgpu.edge_costs(states, y, x, radius, obs, [m])
+        assert np.array_equal(abits, rbits)
+        assert np.array_equal(a4.view(np.uint32)[~np.isnan(r4)], r4.view(np.uint32)[~np.isnan(r4)])
+        assert np.array_equal(np.isnan(a4), np.isnan(r4))
+        assert np.array_equal(abest.view(np.uint32), rbest.view(np.uint32))
+        report("edge kernel vs reference cubin (side %g, n %d, m %d, r %g): %d pairs x 4 words bit-identical, "
+               "%d words collide" % (side, n, m, radius, len(y), int(np.unpackbits(((abits >> 4) & 15).astype(np.uint8)).sum())))
+
+
+# ------------------------------------------------------------------------------------------------
+# whole plans
+# ------------------------------------------------------------------------------------------------
+def _compare_plan(g, ref_status, ref_iters, ref_parent, ref_cost, ref_trace, states, tag, exact_cost=False):
+    assert (g.status, g.iterations) == (ref_status, ref_iters), tag
+    assert len(g.trace) == len(ref_trace)
+    for k, (a, b) in enumerate(zip(g.trace, ref_trace)):
+        assert (a["gSize"], a["ySize"], a["xSize"]) == (int(b["gSize"]), int(b["ySize"]), int(b["xSize"])), (tag, k)
+        for key in ("G", "Y", "X"):
+            if key in b:
+                assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (tag, k, key)
+    parent, cost = g.parent, g.dev_cost
+    assert np.array_equal(np.isfinite(cost), np.isfinite(ref_cost)), tag
+    fin = np.isfinite(ref_cost)
+    if exact_cost:
+        assert np.array_equal(cost.view(np.uint32), ref_cost.view(np.uint32)), tag
+        assert np.array_equal(parent, ref_parent), tag
+        return
+    np.testing.assert_allclose(cost[fin], ref_cost[fin], rtol=RTOL, err_msg=tag)
+    diff = np.flatnonzero(parent != ref_parent)
+    # a parent may differ from the CPU oracle only where two candidates tie to within rounding
+    for i in diff:
+        assert abs(cost[i] - ref_cost[i]) <= RTOL * max(1.0, abs(ref_cost[i])), (tag, int(i))
+    report("%s: %d parents differ from the CPU oracle (ties within %g), of %d connected"
+          % (tag, len(diff), RTOL, int(fin.sum())))
+    assert len(diff) <= max(2, int(0.002 * fin.sum())), tag
+
+
+@pytest.mark.parametrize("n,m,seed,mode", [(2000, 20, 19, "uniform"), (1200, 0, 5, "uniform"),
+                                          (1500, 40, 7, "uniform"), (7 * 196, 10, 3, "lattice")])
+def test_plan_matches_cpu_oracle(GMT, oracles, n, m, seed, mode):
+    """BASELINE config 1 (2k samples / 20 obstacles) and variations against the C oracle."""
+    init, it, meta = _world(None, n, m, seed, mode)
+    g = GMT(init)
+    route = g.run_step(it, iter_limit=200, debug=True)
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=200)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'],
+                  "n=%d m=%d %s" % (n, m, mode))
+    if r["route"]:
+        assert len(route) == len(r["route"])
+        gc = g.dev_cost[it['goal']]
+        assert abs(gc - r["cost"][it['goal']]) <= RTOL * r["cost"][it['goal']]
+
+
+def test_plan_bit_exact_vs_reference_kernels_on_gpu(GMT, refgpu):
+    """The reference's kernels under the restated GMT.run_step loop, on this GPU: everything equal."""
+    from oracle.gmt_oracle import OracleGMT
+    init, it, meta = _world(None, 900, 12, 23)
+    ref = OracleGMT(init, refgpu)
+    rroute = ref.run_step(it, iter_limit=60)
+    g = GMT(init)
+    route = g.run_step(it, iter_limit=60, debug=True)
+    _compare_plan(g, ref.status, ref.iterations, ref.parent, ref.dev_cost, ref.trace, init['states'],
+                  "vs reference cubin", exact_cost=True)
+    assert route == [int(v) for v in rroute]
+    report("plan vs reference kernels on this GPU (n 900, m 12): status %d, %d wavefronts, %d connected nodes: "
+           "sets, parents and cost bit patterns identical" % (g.status, g.iterations, int((g.parent >= 0).sum())))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases the reference's control flow has (gmt_planner.py:143-158, 68-69)
+# ------------------------------------------------------------------------------------------------
+def test_exits_and_stale_route_semantics(GMT, oracles):
+    init, it, meta = _world(None, 600, 6, 31)
+    g = GMT(init)
+    # iter_limit = 1: first turn hits the limit before anything is connected
+    assert g.run_step(it, iter_limit=1) == [] and g.status == 1 and g.iterations == 1
+    assert (g.parent == -1).all()
+    full = list(g.run_step(it, iter_limit=200))
+    assert g.status == 0 and full[0] == it['goal'] and full[-1] == it['start']
+    # same start again, limit too small: the previous route comes back unchanged
+    assert g.run_step(it, iter_limit=2) == full and g.status == 1
+    # different start + failure: the reference drops the last element of the stale route
+    it2 = dict(it)
+    it2['start'] = full[-2]
+    stale = g.run_step(it2, iter_limit=1)
+    assert stale == full[:-1]
+    # start == goal: goal is in the first wavefront
+    it3 = dict(it)
+    it3['start'] = it3['goal']
+    assert g.run_step(it3, iter_limit=50) == [it['goal']] and g.iterations == 1 and g.status == 0
+
+
+def test_unreachable_goal_runs_to_the_limit(GMT, oracles):
+    """No empty-open exit in the reference: an isolated goal spins to iter_limit."""
+    init, it, meta = _world(None, 500, 0, 41, reachable=False)
+    nbr, num = init['neighbors'], init['num_neighbors'].copy()
+    # cut the goal out of every neighbour list
+    goal = it['goal']
+    keep = nbr != goal
+    rows = np.repeat(np.arange(len(num)), num)
+    num2 = np.bincount(rows[keep], minlength=len(num)).astype(np.int32)
+    init2 = dict(init, neighbors=nbr[keep].astype(np.int32), num_neighbors=num2)
+    g = GMT(init2)
+    route = g.run_step(it, iter_limit=80, debug=True)
+    r = oracles["cuda"].plan(init2['states'], init2['neighbors'], init2['num_neighbors'], it['start'], goal,
+                             it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=80)
+    assert route == [] and g.status == 1 and g.iterations == 80 == r["iterations"]
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "unreachable")
+
+
+def test_start_inside_an_obstacle_connects_everything_at_1e10(GMT, oracles):
+    """Every word out of a boxed-in start collides: neighbours get cost 1e10 and parent start
+    (kernel.py:419-427), nothing ever enters the wavefront again."""
+    init, it, meta = _world(None, 500, 0, 43)
+    s = init['states'][it['start']]
+    obs = np.array([[s[0] - 1.5, s[1] - 1.5, s[0] + 1.5, s[1] + 1.5]], np.float32)
+    it = dict(it, obstacles=obs, num_obs=np.array([1], np.int32))
+    g = GMT(init)
+    g.run_step(it, iter_limit=12, debug=True)
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             it['radius'], it['threshold'], obs, [1], iter_limit=12)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "boxed start")
+    assert (g.dev_cost[np.isfinite(g.dev_cost) & (g.dev_cost > 0)] >= 1e10).all()
+
+
+def test_replanning_on_one_instance(GMT, oracles):
+    """cuda_agent.py:218 re-plans on the same GMT instance with a new start and new obstacles."""
+    init, it, meta = _world(None, 800, 10, 47)
+    g = GMT(init)
+    r1 = list(g.run_step(it, iter_limit=200))
+    it2 = dict(it, start=r1[-3] if len(r1) > 3 else it['start'])
+    rng = np.random.default_rng(1)
+    obs2 = it['obstacles'][rng.permutation(len(it['obstacles']))[:5]]
+    it2.update(obstacles=obs2, num_obs=np.array([5], np.int32))
+    g.run_step(it2, iter_limit=200, debug=True)
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it2['start'], it2['goal'],
+                             it2['radius'], it2['threshold'], obs2, [5], iter_limit=200)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "re-plan")
+    # and the first query again gives the first answer again (no state leaks between plans)
+    assert list(g.run_step(it, iter_limit=200)) == r1
+
+
+# ------------------------------------------------------------------------------------------------
+# roadmap builders
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,n,side", [("uniform", 20000, 190.7), ("lattice", 7 * 900, 116.0), ("uniform", 1, 3.0)])
+def test_sampler_and_neighbour_search_bit_exact(gmt_lib, mode, n, side):
+    import synthetic_world as sw
+    from oracle.world_oracle import build_neighbors, sample_states
+    a = sw.cuda_sampler(77, n, side, mode)
+    b = sample_states(77, n, side, mode)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    nbr, num = sw.cuda_neighbor_builder(a)
+    onbr, onum = build_neighbors(b)
+    assert np.array_equal(num, onum) and np.array_equal(nbr, onbr)
+
+
+# ------------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties (the CPU oracle would take minutes)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("config", [2, 3])
+def test_full_size_plan_properties(GMT, gmt_lib, config):
+    import synthetic_world as sw
+    init, it, meta = sw.make_world(config)
+    it = dict(it, goal=sw.pick_reachable_goal(init, it, meta["side"]))
+    states = init['states']
+    g = GMT(init)
+    route = list(g.run_step(it, iter_limit=1000))
+    res = g.last_result
+    parent, cost = g.parent.copy(), g.dev_cost.copy()
+    assert g.status in (0, 1)
+    # idempotence: the same query gives the same tree, bit for bit
+    route2 = list(g.run_step(it, iter_limit=1000))
+    assert route2 == route and np.array_equal(g.parent, parent)
+    assert np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
+    # the tree is a tree rooted at start: every connected node reaches start, costs grow along it
+    conn = np.flatnonzero(parent >= 0)
+    assert parent[it['start']] == -1 and cost[it['start']] == 0
+    assert np.isfinite(cost[conn]).all()
+    assert (cost[conn] >= cost[parent[conn]]).all()
+    # a Dubins edge is never shorter than the straight line (checked with float slack)
+    d = np.hypot(states[conn, 0] - states[parent[conn], 0], states[conn, 1] - states[parent[conn], 1])
+    free = cost[conn] < 1e9
+    assert (cost[conn][free] - cost[parent[conn]][free] >= d[free] * (1 - 1e-4) - 1e-2).all()
+    if g.status == 0:
+        assert route[0] == it['goal'] and route[-1] == it['start']
+        for a, b in zip(route[:-1], route[1:]):
+            assert parent[a] == b
+        # every edge of the route, re-evaluated by the edge kernel, is collision free and has the tree's cost
+        y = np.array(route[1:], np.int32)
+        x = np.array(route[:-1], np.int32)
+        m = int(it['num_obs'][0])
+        _, bits, best = _edge(gmt_lib, states, init['neighbors'], init['num_neighbors'], it['obstacles'], m, y, x,
+                              it['radius'])
+        step = cost[x] - cost[y]
+        np.testing.assert_allclose(best, step, rtol=1e-4, atol=1e-3)
+        assert (best < 1e9).all()
+    report("config %d: status %d, %d iterations, %.3f ms on device, %d edge pairs, %d evaluated, %d swept"
+          % (config, g.status, g.iterations, res.device_ms, res.edge_pairs, res.edge_evals, res.word_checks))
+
+
+def test_resident_obstacles_give_the_same_plan(GMT, gmt_lib):
+    import _lib
+    import synthetic_world as sw
+    init, it, meta = sw.make_world(1)
+    g = GMT(init)
+    route = list(g.run_step(it, iter_limit=300))
+    parent = g.parent.copy()
+    obs = np.ascontiguousarray(it['obstacles'], np.float32)
+    m = int(it['num_obs'][0])
+    _lib.check(gmt_lib.gmt_set_obstacles(g._handle, obs.ctypes.data, m), "gmt_set_obstacles")
+    res = _lib.GmtResult()
+    _lib.check(gmt_lib.gmt_plan_resident(g._handle, it['start'], it['goal'], 2.0, 1.0, 300, C.byref(res)), "plan")
+    out = np.zeros(g.n, np.int32)
+    _lib.check(gmt_lib.gmt_get_parent(g._handle, out.ctypes.data), "parent")
+    assert np.array_equal(out, parent) and res.route_len == len(route)
