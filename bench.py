@@ -63,17 +63,28 @@ class ClockSampler:
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, gpu_id):
-        self.gpu_id, self.proc, self.path = gpu_id, None, None
+        self.gpu_id, self.proc, self.path, self.skip = gpu_id, None, None, 0
 
     def start(self):
+        """Starts polling (50 ms) and waits until the first sample is there (nvidia-smi needs a moment)."""
         try:
             fd, self.path = tempfile.mkstemp(prefix="gmt_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_id), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            while time.time() - t0 < 3.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken before this call (warm-up) are not part of the timed region."""
+        try:
+            self.skip = sum(1 for _ in open(self.path))
+        except Exception:
+            self.skip = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -86,7 +97,10 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            lines = open(self.path).read().splitlines()
+            if len(lines) > self.skip:        # keep only the timed region unless it was too short to be sampled
+                lines = lines[self.skip:]
+            for line in lines:
                 parts = [p.strip() for p in line.split(",")]
                 if len(parts) < 7:
                     continue
@@ -186,8 +200,10 @@ def run_reference(args):
     backend, kind, cores = cpu_backend()
     total = workload_meta(args.config).get("edge_pairs", 0)
     vals, desc = [], ""
+    # every step is a bounded sample; the whole run stays within a few minutes whatever K is
+    budget = min(args.cpu_budget, 150.0 / max(args.warmup + args.steps, 1))
     for s in range(args.warmup + args.steps):
-        v, desc = cpu_sample(init, it, backend, args.cpu_budget, total)
+        v, desc = cpu_sample(init, it, backend, budget, total)
         if s >= args.warmup:
             vals.append(v)
         log("reference step %d: %.6g plans/s (%s)" % (s, v, desc))
@@ -254,13 +270,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        plan_resident()
-        g.run_step(it, iter_limit=1000)
     props = torch.cuda.get_device_properties(dev)
     gpu_id = "GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local)
     sampler = ClockSampler(gpu_id)
     sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        plan_resident()
+        g.run_step(it, iter_limit=1000)
+    sampler.mark()
 
     # ---- value: resident inputs ---------------------------------------------------------------
     K = args.steps
@@ -296,10 +313,8 @@ def run_b200(args):
     t_e2e = max(sum(a.elapsed_time(b) for a, b in ev2) * 1e-3, wall)
     clocks = sampler.stop()
 
-    if dist is not None:
-        t = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_value, t_e2e = float(t[0]), float(t[1])
+    import multi_gpu
+    t_value, t_e2e = multi_gpu.max_over_ranks([t_value, t_e2e], device=dev)     # slowest rank
 
     # ---- edge kernel in isolation (the "Dubins edge checks/sec" half of the metric) -------------
     edge = None
@@ -381,7 +396,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -69,10 +69,10 @@ def world_side(n):
     return math.sqrt(n / DENSITY)
 
 
-def make_obstacles(rng, m, side, layout, keep_out):
-    """m AABBs [xa, ya, xb, yb]; rejected while they contain one of the keep_out points."""
+def make_obstacles(rng, m, side, layout):
+    """m AABBs [xa, ya, xb, yb] with half-extents U[1,5] m, stored as two opposite corners in
+    arbitrary order like the reference does (cuda_agent.py:197)."""
     boxes = []
-    keep_out = np.asarray(keep_out, np.float64).reshape(-1, 2)
     while len(boxes) < m:
         c = rng.uniform(0.0, side, 2)
         if layout == "roads":
@@ -82,10 +82,6 @@ def make_obstacles(rng, m, side, layout, keep_out):
                 continue
         h = rng.uniform(1.0, 5.0, 2)
         lo, hi = c - h, c + h
-        inside = np.all((keep_out >= lo - 0.5) & (keep_out <= hi + 0.5), axis=1)
-        if inside.any():
-            continue
-        # the reference stores two opposite corners in arbitrary order (cuda_agent.py:197)
         if rng.random() < 0.5:
             boxes.append([hi[0], hi[1], lo[0], lo[1]])
         else:
@@ -93,6 +89,27 @@ def make_obstacles(rng, m, side, layout, keep_out):
     if m == 0:
         return np.array([[-1, -1, -1, -1]]).astype(np.float32), np.array([0]).astype(np.int32)
     return np.array(boxes).astype(np.float32), np.array([m]).astype(np.int32)
+
+
+def clearance(points, obstacles, m):
+    """Distance from each (x, y) to the nearest of the first m boxes (0 inside a box)."""
+    pts = np.asarray(points, np.float64).reshape(-1, 2)
+    if m == 0:
+        return np.full(len(pts), np.inf)
+    obs = np.asarray(obstacles, np.float64)[:m]
+    lo = np.minimum(obs[:, :2], obs[:, 2:])
+    hi = np.maximum(obs[:, :2], obs[:, 2:])
+    d = np.maximum(np.maximum(lo[None] - pts[:, None], pts[:, None] - hi[None]), 0.0)
+    return np.hypot(d[..., 0], d[..., 1]).min(axis=1)
+
+
+def nearest_clear_state(states, x, y, obstacles, m, clear=4.0, tries=2000):
+    """The state nearest (x, y) that keeps `clear` metres from every box (the reference starts from a
+    driving car, never from inside a parked one); falls back to the plain nearest state."""
+    d = (states[:, 0].astype(np.float64) - x) ** 2 + (states[:, 1].astype(np.float64) - y) ** 2
+    order = np.argsort(d, kind="stable")[:tries]
+    ok = clearance(states[order, :2], obstacles, m) >= clear
+    return int(order[np.argmax(ok)]) if ok.any() else int(order[0])
 
 
 def nearest_state(states, x, y):
@@ -116,10 +133,10 @@ def make_world(config=None, n=None, m=None, mode=None, layout=None, seed=None, s
     states = np.ascontiguousarray(sampler(seed, n, side, mode), np.float32)
     n = states.shape[0]
     neighbors, num_neighbors = neighbor_builder(states, DISK_RADIUS)
-    start = nearest_state(states, 0.1 * side, 0.1 * side)
-    goal = nearest_state(states, 0.9 * side, 0.9 * side)
     rng = np.random.default_rng(seed)
-    obstacles, num_obs = make_obstacles(rng, m, side, layout, [states[start, :2], states[goal, :2]])
+    obstacles, num_obs = make_obstacles(rng, m, side, layout)
+    start = nearest_clear_state(states, 0.1 * side, 0.1 * side, obstacles, m)
+    goal = nearest_clear_state(states, 0.9 * side, 0.9 * side, obstacles, m)
 
     init_parameters = {'states': states, 'neighbors': neighbors, 'num_neighbors': num_neighbors,
                        'threadsPerBlock': 128}

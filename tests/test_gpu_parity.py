@@ -368,3 +368,28 @@ def test_resident_obstacles_give_the_same_plan(GMT, gmt_lib):
     out = np.zeros(g.n, np.int32)
     _lib.check(gmt_lib.gmt_get_parent(g._handle, out.ctypes.data), "parent")
     assert np.array_equal(out, parent) and res.route_len == len(route)
+
+
+def test_plan_batch_equals_single_plans(GMT, gmt_lib):
+    """gmt_plan_batch (BASELINE config 4's entry: many start/goal queries on one roadmap, obstacles resident)."""
+    import _lib
+    import synthetic_world as sw
+    init, it, meta = sw.make_world(1)
+    g = GMT(init)
+    starts, goals = sw.make_queries(init['states'], meta["side"], 6, 5)
+    singles = [list(g.run_step(dict(it, start=int(a), goal=int(b)), iter_limit=120)) for a, b in zip(starts, goals)]
+    obs = np.ascontiguousarray(it['obstacles'], np.float32)
+    _lib.check(gmt_lib.gmt_set_obstacles(g._handle, obs.ctypes.data, int(it['num_obs'][0])), "gmt_set_obstacles")
+    res = (_lib.GmtResult * 6)()
+    stride = 256
+    routes = np.zeros((6, stride), np.int32)
+    _lib.check(gmt_lib.gmt_plan_batch(g._handle, starts.ctypes.data, goals.ctypes.data, 6, 2.0, 1.0, 120, res,
+                                      routes.ctypes.data, stride), "gmt_plan_batch")
+    for k in range(6):
+        want = singles[k] if res[k].route_len >= 0 else []
+        got = [int(v) for v in routes[k, :max(res[k].route_len, 0)]]
+        # a fresh GMT instance has no stale route; the batch call reports route_len = -1 for failures
+        if res[k].status == 0:
+            assert got == singles[k]
+        else:
+            assert res[k].route_len == -1 or got == want
