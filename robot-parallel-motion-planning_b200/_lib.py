@@ -15,7 +15,7 @@ class GmtResult(C.Structure):
     _fields_ = [("status", C.c_int), ("iterations", C.c_int), ("goal_cost", C.c_float),
                 ("route_len", C.c_int), ("device_ms", C.c_float), ("grid_overflow", C.c_int),
                 ("edge_pairs", C.c_longlong), ("edge_evals", C.c_longlong),
-                ("word_checks", C.c_longlong), ("launches", C.c_int), ("reserved", C.c_int)]
+                ("word_checks", C.c_longlong), ("launches", C.c_int), ("farthest_frontier", C.c_int)]
 
 
 class GmtError(RuntimeError):

@@ -183,3 +183,31 @@ def make_queries(states, side, q, seed):
             starts.append(a)
             goals.append(b)
     return np.array(starts, np.int32), np.array(goals, np.int32)
+
+
+def plan_batch(handle_owner, starts, goals, radius=2.0, threshold=1.0, iter_limit=1000, route_stride=0):
+    """gmt_plan_batch on the GMT instance's handle (obstacles must be resident: gmt_set_obstacles).
+    Returns (results ctypes array, routes int32[q, route_stride] or None)."""
+    lib = _lib.load()
+    starts = np.ascontiguousarray(starts, np.int32)
+    goals = np.ascontiguousarray(goals, np.int32)
+    q = len(starts)
+    res = (_lib.GmtResult * q)()
+    routes = np.zeros((q, route_stride), np.int32) if route_stride > 0 else None
+    rc = lib.gmt_plan_batch(handle_owner._handle, starts.ctypes.data, goals.ctypes.data, q, float(np.float32(radius)),
+                            float(np.float32(threshold)), int(iter_limit), res,
+                            routes.ctypes.data if routes is not None else None, int(route_stride))
+    _lib.check(rc, "gmt_plan_batch")
+    return res, routes
+
+
+def make_reachable_queries(gmt, n, q, seed, radius=2.0, threshold=1.0, iter_limit=1000):
+    """q independent queries for BASELINE config 4: starts drawn uniformly; each goal is the state that
+    enters a wavefront farthest (straight line) from its start -- found with one goal-less batch
+    (gmt_result.farthest_frontier), so that every query ends with "goal reached"."""
+    rng = np.random.default_rng(seed)
+    starts = rng.integers(0, n, q).astype(np.int32)
+    res, _ = plan_batch(gmt, starts, np.full(q, -1, np.int32), radius, threshold, iter_limit)
+    goals = np.array([r.farthest_frontier if r.farthest_frontier >= 0 else int(s) for r, s in zip(res, starts)],
+                     np.int32)
+    return starts, goals
