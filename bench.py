@@ -39,7 +39,8 @@ for _p in (ROOT, PKG):
 
 METRIC = "gmt_plans_per_sec"
 UNIT = "plans/s"
-WORKLOADS = {1: "cfg1: single query, 2k samples, 20 obstacles",
+WORKLOADS = {4: "cfg4: batch of 4096 independent start/goal queries on a 10k-sample map, sharded by rank, no collective",
+             1: "cfg1: single query, 2k samples, 20 obstacles",
              2: "cfg2: single query, 10k samples, 100 obstacles",
              3: "cfg3: single query, 100k samples, road lattice, 2k obstacles"}
 
@@ -249,12 +250,9 @@ def run_b200(args):
     g = GMT(init, device=local)
     stream = torch.cuda.current_stream(dev)
     _lib.check(lib.gmt_set_stream(g._handle, C.c_void_p(stream.cuda_stream)), "gmt_set_stream")
-    # one independent query per rank: rank 0 plans the configuration's own start/goal
+    # weak scaling: every rank plans the configuration's query on its own replica of the roadmap --
+    # independent plans, identical work per GPU, nothing exchanged on the data path
     start, goal = int(it['start']), int(it['goal'])
-    if rank > 0:
-        qs, qg = sw.make_queries(init['states'], meta["side"], world, meta["seed"] + 1000)
-        start, goal = int(qs[rank]), int(qg[rank])
-    it = dict(it, start=start, goal=goal)
     obs = np.ascontiguousarray(it['obstacles'], np.float32)
     radius, thr0 = float(np.float32(it['radius'])), float(np.float32(it['threshold']))
     _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
@@ -351,6 +349,7 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config], "n": n, "m": m, "seed": meta["seed"],
                    "mean_degree": round(meta["mean_degree"], 2), "queries_per_step_per_gpu": 1,
+                   "multi_gpu": "each rank plans this query independently on its own replica (no collective)",
                    "l2": "flushed between timed plans (256 MiB fill)", "iter_limit": 1000,
                    "plan": {"status": status, "wavefronts": iterations, "goal_cost": goal_cost,
                             "route_len": len(route), "edge_checks": pairs, "pairs_evaluated": evals,
@@ -393,6 +392,85 @@ def run_b200(args):
     return 0
 
 
+def run_b200_batch(args):
+    """BASELINE config 4: 4096 independent queries on one 10k map; each rank plans its contiguous share
+    with gmt_plan_batch (one launch, teams of blocks); strong scaling, no collective on the data path."""
+    import ctypes as C
+
+    import torch
+    import _lib
+    import multi_gpu
+    import synthetic_world as sw
+    from gmt_planner import GMT
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the planner has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    Q = 4096
+    init, it, meta = sw.make_world(4)
+    n, m = meta["n"], meta["m"]
+    g = GMT(init, device=local)
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(lib.gmt_set_stream(g._handle, C.c_void_p(stream.cuda_stream)), "gmt_set_stream")
+    obs = np.ascontiguousarray(it['obstacles'], np.float32)
+    _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
+    starts, goals = sw.make_reachable_queries(g, n, Q, meta["seed"] + 7)       # same list on every rank
+    s, gl = multi_gpu.shard_queries(starts, goals, rank, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        res, _r = sw.plan_batch(g, s, gl)
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches, kern_ms = 0, 0.0
+    barrier()
+    for k in range(K):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        res, routes = sw.plan_batch(g, s, gl, route_stride=128)      # host buffers in, results + routes out
+        ev[k][1].record(stream)
+        launches += res[0].launches
+        kern_ms += res[0].device_ms
+    barrier()
+    t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    (t,) = multi_gpu.max_over_ranks([t], device=dev)
+    reached = sum(r.status == 0 for r in res)
+    pairs = sum(r.edge_pairs for r in res)
+    if rank == 0:
+        value = Q * K / t
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": max(args.warmup, 3), "ms_per_step": t / K * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS[4], "n": n, "m": m, "seed": meta["seed"], "queries": Q,
+                           "queries_per_rank": len(s), "l2": "flushed between timed batches (256 MiB fill)",
+                           "goal_reached_rank0": reached, "edge_checks_rank0": pairs},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * len(s)),
+                        "d2h_bytes_per_step": int(len(s) * (136 + 4 * 128)),
+                        "note": "the batch call takes host start/goal arrays and returns host results + routes: value is e2e"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "unit": "TFLOP/s", "traffic": None,
+                             "achieved": pairs * f_edge(m) / (kern_ms / K * 1e-3) * 1e-12, "peak": None, "frac": None,
+                             "kernel_ms": kern_ms / K}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -404,7 +482,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.config == 4:
+            args.config = 2          # the CPU arm times one query of the same kind of map
         return run_reference(args)
+    if args.config == 4:
+        if args.steps == 200:
+            args.steps = 5
+        return run_b200_batch(args)
     return run_b200(args)
 
 
