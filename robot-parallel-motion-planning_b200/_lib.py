@@ -42,6 +42,10 @@ PROTOTYPES = {
                                  C.POINTER(C.c_longlong)]),
     "gmt_free": (None, [_vp]),
     "gmt_plan_batch": (_i, [_vp, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _i]),
+    "gmt_sharded_begin": (_i, [_vp, _i, _i, _f, _f, _i, _i, _i]),
+    "gmt_sharded_step": (_i, [_vp, _ip]),
+    "gmt_best_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(C.c_longlong)]),
+    "gmt_sharded_finish": (_i, [_vp, C.POINTER(GmtResult)]),
     "gmt_measure_fp32_peak": (_i, [_i, _fp]),
     "gmt_last_error": (C.c_char_p, []),
     "gmt_version": (_i, []),

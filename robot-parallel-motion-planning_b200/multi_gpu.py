@@ -49,3 +49,124 @@ def plan_queries(gmt, iter_parameters, starts, goals, iter_limit=1000):
     for s, g in zip(starts, goals):
         routes.append(list(gmt.run_step(dict(iter_parameters, start=int(s), goal=int(g)), iter_limit=iter_limit)))
     return routes
+
+
+# ------------------------------------------------------------------------------------------------------
+# Single very large roadmap, sharded by node range (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------------
+class _DeviceArray(object):
+    """Minimal __cuda_array_interface__ holder so torch can alias memory the library owns."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def best_tensor(gmt):
+    """int64 torch tensor aliasing the planner's packed (cost bits << 32 | parent) array on the device.
+    All keys are < 2^63 (cost >= 0), so the signed integer order is the unsigned one the kernels use."""
+    import ctypes as C
+
+    import torch
+    try:
+        from . import _lib
+    except ImportError:
+        import _lib
+    ptr, count = C.c_void_p(), C.c_longlong()
+    _lib.check(gmt._lib.gmt_best_dev(gmt._handle, C.byref(ptr), C.byref(count)), "gmt_best_dev")
+    return torch.as_tensor(_DeviceArray(ptr.value, count.value, "<i8"), device="cuda")
+
+
+def allreduce_min(t):
+    """The per-wavefront exchange: NCCL all-reduce(min) of the packed cost/parent array over NVLink."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+
+
+def run_step_sharded(gmt, iter_parameters, iter_limit=1000, rank=0, world=1, exchange=allreduce_min):
+    """GMT.run_step for one roadmap sharded over `world` GPUs: this rank connects the candidate nodes with
+    ids in its contiguous range; after every wavefront the packed cost/parent arrays are min-reduced.
+    Every rank returns the same route.  Returns (route, gmt_result, wavefront launches)."""
+    import ctypes as C
+
+    import numpy as np
+    try:
+        from . import _lib
+    except ImportError:
+        import _lib
+    lib = gmt._lib
+    gmt.step_init(iter_parameters, False)
+    num_obs = int(np.asarray(iter_parameters['num_obs']).reshape(-1)[0])
+    obs = np.ascontiguousarray(iter_parameters['obstacles'], dtype=np.float32).reshape(-1, 4)
+    _lib.check(lib.gmt_set_obstacles(gmt._handle, obs.ctypes.data if num_obs > 0 else None, num_obs), "gmt_set_obstacles")
+    lo, hi = shard_range(gmt.n, rank, world)
+    _lib.check(lib.gmt_sharded_begin(gmt._handle, int(gmt.start), int(gmt.goal), float(np.float32(gmt.radius)),
+                                     float(gmt.threshold[0]), int(iter_limit), lo, hi), "gmt_sharded_begin")
+    best = best_tensor(gmt)
+    status, steps = C.c_int(-2), 0
+    while True:
+        _lib.check(lib.gmt_sharded_step(gmt._handle, C.byref(status)), "gmt_sharded_step")
+        steps += 1
+        if status.value != -2:
+            break
+        exchange(best)
+    res = _lib.GmtResult()
+    _lib.check(lib.gmt_sharded_finish(gmt._handle, C.byref(res)), "gmt_sharded_finish")
+    gmt.last_result, gmt.iterations, gmt.status = res, res.iterations, res.status
+    if res.status == _lib.GMT_STATUS_GOAL or res.route_len >= 0:
+        gmt.route = []
+        gmt.get_path()
+    return gmt.route, res, steps
+
+
+def run_step_sharded_emulated(gmts, iter_parameters, iter_limit=1000):
+    """The same protocol with all ranks emulated in ONE process on ONE GPU (len(gmts) handles on the same
+    roadmap): used by the GPU tests, where more ranks than GPUs must not spin on each other."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    try:
+        from . import _lib
+    except ImportError:
+        import _lib
+    world = len(gmts)
+    bests = []
+    for r, g in enumerate(gmts):
+        g.step_init(iter_parameters, False)
+        num_obs = int(np.asarray(iter_parameters['num_obs']).reshape(-1)[0])
+        obs = np.ascontiguousarray(iter_parameters['obstacles'], dtype=np.float32).reshape(-1, 4)
+        _lib.check(g._lib.gmt_set_obstacles(g._handle, obs.ctypes.data if num_obs > 0 else None, num_obs), "obs")
+        lo, hi = shard_range(g.n, r, world)
+        _lib.check(g._lib.gmt_sharded_begin(g._handle, int(g.start), int(g.goal), float(np.float32(g.radius)),
+                                            float(g.threshold[0]), int(iter_limit), lo, hi), "begin")
+        bests.append(best_tensor(g))
+    steps = 0
+    while True:
+        stats = []
+        for g in gmts:
+            st = C.c_int()
+            _lib.check(g._lib.gmt_sharded_step(g._handle, C.byref(st)), "step")
+            stats.append(st.value)
+        steps += 1
+        assert len(set(stats)) == 1, "ranks disagree on the plan state: %r" % (stats,)
+        if stats[0] != -2:
+            break
+        torch.cuda.synchronize()
+        m = bests[0].clone()
+        for b in bests[1:]:
+            m = torch.minimum(m, b)
+        for b in bests:
+            b.copy_(m)
+        torch.cuda.synchronize()
+    out = []
+    for g in gmts:
+        res = _lib.GmtResult()
+        _lib.check(g._lib.gmt_sharded_finish(g._handle, C.byref(res)), "finish")
+        g.last_result, g.iterations, g.status = res, res.iterations, res.status
+        if res.status == _lib.GMT_STATUS_GOAL or res.route_len >= 0:
+            g.route = []
+            g.get_path()
+        out.append((list(g.route), res))
+    return out, steps

@@ -393,3 +393,23 @@ def test_plan_batch_equals_single_plans(GMT, gmt_lib):
             assert got == singles[k]
         else:
             assert res[k].route_len == -1 or got == want
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_node_range_sharding_equals_single_plan(GMT, world):
+    """BASELINE config 5's protocol (every rank connects only its node range, min-reduce of the packed
+    cost/parent array after every wavefront) with the ranks emulated in one process on this GPU."""
+    import multi_gpu
+    init, it, meta = _world(None, 3000, 30, 61)
+    ref = GMT(init)
+    route = list(ref.run_step(it, iter_limit=300))
+    parent, cost = ref.parent.copy(), ref.dev_cost.copy()
+    ranks = [GMT(init) for _ in range(world)]
+    out, steps = multi_gpu.run_step_sharded_emulated(ranks, it, iter_limit=300)
+    for g, (r, res) in zip(ranks, out):
+        assert (res.status, res.iterations) == (ref.status, ref.iterations)
+        assert r == route
+        assert np.array_equal(g.parent, parent)
+        assert np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
+    report("node-range sharding, %d emulated ranks: %d wavefront launches, tree identical to the single-GPU plan "
+           "(%d connected nodes)" % (world, steps, int((parent >= 0).sum())))
