@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgmt_b200.so")
+LIB_PATH = os.environ.get("GMT_B200_LIB") or os.path.join(HERE, "libgmt_b200.so")   # override: tuning builds only
 
 GMT_OK = 0
 GMT_STATUS_GOAL = 0

@@ -4,11 +4,15 @@ sys.path.insert(0, '.'); sys.path.insert(0, 'robot-parallel-motion-planning_b200
 import _lib, synthetic_world as sw
 from gmt_planner import GMT
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-init, it, meta = sw.make_world(cfg)
-if len(sys.argv) > 2:
-    it = dict(it, goal=int(sys.argv[2]))
-else:
+if cfg == 0:      # explicit sizes: dbg_phases.py 0 <n> <m>
+    init, it, meta = sw.make_world(n=int(sys.argv[2]), m=int(sys.argv[3]), seed=23)
     it = dict(it, goal=sw.pick_reachable_goal(init, it, meta["side"]))
+else:
+    init, it, meta = sw.make_world(cfg)
+    if len(sys.argv) > 2:
+        it = dict(it, goal=int(sys.argv[2]))
+    else:
+        it = dict(it, goal=sw.pick_reachable_goal(init, it, meta["side"]))
 g = GMT(init)
 for rep in range(3):
     route = g.run_step(it, iter_limit=1000, time=True)
@@ -31,3 +35,4 @@ for bps, thr in ((1, 128), (1, 256), (1, 512), (2, 256), (4, 128), (8, 64)):
     us = C.c_float()
     g._lib.gmt_debug_barrier_us(g._handle, bps, thr, 2000, C.byref(us))
     print('grid barrier: %d blocks/SM x %d threads: %.2f us' % (bps, thr, us.value))
+print('sweep outcomes in the sweep phase: free %d, hit in first arc round %d, hit later %d' % (v[5], v[6], v[7]))
