@@ -413,3 +413,23 @@ def test_node_range_sharding_equals_single_plan(GMT, world):
         assert np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
     report("node-range sharding, %d emulated ranks: %d wavefront launches, tree identical to the single-GPU plan "
            "(%d connected nodes)" % (world, steps, int((parent >= 0).sum())))
+
+
+def test_blocked_arrival_masks_do_not_change_results(GMT, oracles, monkeypatch):
+    """The blocked-arrival masks (exact rejection of words whose last stretch into a 'hard' x lies inside a
+    box) are normally used for large fronts and batches only; force them on for a cluttered 2k world and
+    compare with the CPU oracle, then force them off and compare the two GPU runs bit for bit."""
+    init, it, meta = _world(None, 3000, 30, 61)
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=200)
+    monkeypatch.setenv("GMT_MASK_MIN_Y", "0")
+    g = GMT(init)
+    g.run_step(it, iter_limit=200, debug=True)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "masks on")
+    parent_on, cost_on, swept_on = g.parent.copy(), g.dev_cost.copy(), g.last_result.word_checks
+    monkeypatch.setenv("GMT_MASK_MIN_Y", "1000000")
+    g.run_step(it, iter_limit=200)
+    assert np.array_equal(g.parent, parent_on)
+    assert np.array_equal(g.dev_cost.view(np.uint32), cost_on.view(np.uint32))
+    report("blocked-arrival masks on a 3k world (30 boxes): identical tree with and without; "
+           "words tested %d (on) vs %d (off)" % (swept_on, g.last_result.word_checks))
