@@ -361,7 +361,7 @@ def run_b200(args):
                    "samples": clocks["samples"]},
         "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "achieved": achieved, "peak": fp32_peak.value,
                      "unit": "TFLOP/s", "frac": achieved / fp32_peak.value if fp32_peak.value else None,
-                     "traffic": None, "kernel_ms": kern_s * 1e3,
+                     "traffic": workload_meta(args.config).get("ncu_dram_bytes_per_launch"), "kernel_ms": kern_s * 1e3,
                      "note": "achieved = reference edge checks (sum |X|*|Y| = %d) x F_edge(m=%d) = %.0f op/check "
                              "/ kernel time; peak = FP32 FMA micro-benchmark measured live on this GPU "
                              "(MEASURED_PEAKS.json has no FP32 figure). >1 is expected: exact pruning evaluates "
