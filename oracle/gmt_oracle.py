@@ -48,6 +48,8 @@ class OraclePort:
         L.gmto_word.restype = C.c_int
         L.gmto_word.argtypes = [C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int, C.POINTER(C.c_float),
                                 C.c_void_p, C.c_void_p]
+        L.gmto_word_arcs.restype = C.c_int
+        L.gmto_word_arcs.argtypes = [C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int, C.POINTER(C.c_float), _f32p]
         L.gmto_compute_dubins_cost.restype = C.c_int
         L.gmto_compute_dubins_cost.argtypes = [C.POINTER(C.c_float), C.c_float, _f32p, _f32p, C.c_float,
                                                _f32p, C.c_int]
@@ -81,6 +83,24 @@ class OraclePort:
                                 np.ascontiguousarray(end, np.float32), int(r_min), obs, m,
                                 C.byref(cost), xs.ctypes.data, ys.ctypes.data)
         return fl, cost.value, xs, ys
+
+    def route_edges(self, states, route, radius, obstacles, num_obs):
+        """Trajectory of a goal-first route, start -> goal: (from_to, word, arcs3) like gmt_get_route_edges."""
+        obs, m = _obstacles(obstacles, num_obs)
+        states = np.ascontiguousarray(states, np.float32)
+        path = list(route)[::-1]
+        ft, words, arcs = [], [], []
+        for a, b in zip(path[:-1], path[1:]):
+            bw, bc, ba = 255, np.inf, [np.nan] * 3
+            for w in range(4):
+                cost = C.c_float()
+                a3 = np.zeros(3, np.float32)
+                fl = self.lib.gmto_word_arcs(w, states[a], states[b], int(radius), obs, m, C.byref(cost), a3)
+                if (fl & 1) and not (fl & 2) and cost.value < bc:
+                    bw, bc, ba = w, cost.value, a3.tolist()
+            ft.append((a, b)); words.append(bw); arcs.append(ba)
+        return (np.array(ft, np.int32).reshape(-1, 2), np.array(words, np.uint8),
+                np.array(arcs, np.float32).reshape(-1, 3))
 
     def edge_costs(self, states, y, x, radius, obstacles, num_obs):
         obs, m = _obstacles(obstacles, num_obs)

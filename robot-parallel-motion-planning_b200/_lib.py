@@ -32,10 +32,12 @@ PROTOTYPES = {
     "gmt_set_obstacles": (_i, [_vp, _vp, _i]),
     "gmt_plan_resident": (_i, [_vp, _i, _i, _f, _f, _i, C.POINTER(GmtResult)]),
     "gmt_get_route": (_i, [_vp, _vp, _i, _ip]),
+    "gmt_get_route_edges": (_i, [_vp, _vp, _vp, _vp, _i, _ip]),
     "gmt_get_parent": (_i, [_vp, _vp]),
     "gmt_get_cost": (_i, [_vp, _vp]),
     "gmt_set_trace": (_i, [_vp, _i]),
     "gmt_get_trace": (_i, [_vp, _vp, _i, _vp, C.c_longlong, C.POINTER(C.c_longlong), _vp]),
+    "gmt_get_phase_times": (_i, [_vp, _vp, _i]),
     "gmt_edge_costs": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _fp]),
     "gmt_sample_states": (_i, [C.c_uint, _i, _f, _i, _i, _vp]),
     "gmt_build_neighbors": (_i, [_vp, _i, C.c_double, _i, C.POINTER(_vp), C.POINTER(_vp),

@@ -101,6 +101,19 @@ class GMT(object):
         _lib.check(self._lib.gmt_get_route(self._handle, buf.ctypes.data, cap, C.byref(ln)), "gmt_get_route")
         self.route += [int(v) for v in buf[:ln.value]]
 
+    def route_edges(self):
+        """Trajectory of the last route, start -> goal: arrays (from_to int32[E,2], word uint8[E],
+        arcs float32[E,3] = first arc, straight segment, second arc lengths).  What a controller needs
+        to track the Dubins curve instead of chasing waypoints (reference README.md:257)."""
+        cap = max(len(self.route) - 1, 0)
+        ft = np.zeros((cap, 2), np.int32)
+        word = np.zeros(cap, np.uint8)
+        arcs = np.zeros((cap, 3), np.float32)
+        ln = C.c_int()
+        _lib.check(self._lib.gmt_get_route_edges(self._handle, ft.ctypes.data, word.ctypes.data, arcs.ctypes.data,
+                                                 cap, C.byref(ln)), "gmt_get_route_edges")
+        return ft[:ln.value], word[:ln.value], arcs[:ln.value]
+
     # ---- results the reference downloads (gmt_planner.py:145,152) plus the cost array -----------
     @property
     def parent(self):
@@ -167,6 +180,8 @@ class GMT(object):
         sets = np.zeros(cap, np.int32)
         _lib.check(self._lib.gmt_get_trace(self._handle, sizes.ctypes.data, iterations, sets.ctypes.data,
                                            cap, C.byref(ln), ms.ctypes.data), "gmt_get_trace")
+        ph = np.zeros((max(iterations, 1), 4), np.float32)
+        _lib.check(self._lib.gmt_get_phase_times(self._handle, ph.ctypes.data, iterations), "gmt_get_phase_times")
         self.trace = []
         pos = 0
         for k in range(iterations):
@@ -181,14 +196,19 @@ class GMT(object):
             if debug:
                 print('y size: ', y, 'G size: ', g, 'x size: ', x)
                 print(f'######### iteration: {k + 1} iteration time: {ms[k] * 1e-3}')
-            # the reference only times turns that reach the end of the loop body (gmt_planner.py:229)
+            # the reference only times turns that reach the end of the loop body (gmt_planner.py:229).
+            # Its host timers bracket launches; here each key gets the DEVICE time of the phase that does
+            # that work inside the persistent kernel (seconds, like timeit's):
+            #   wavefront          <- frontier phase (wavefront + growThreshold + goal test + neighborIndicator)
+            #   neighbors_compact  <- select phase (which open nodes can still be a parent of which x)
+            #   connection         <- word lengths + swept paths (dubinConnection)
+            # the scans/compactions of the reference have no counterpart (lists are built in place): 0
             if time and y > 0 and x > 0:
-                # per-phase host timers of the reference have no counterpart inside one persistent
-                # kernel: the device time of the turn is reported as elapsed/connection, rest 0
-                sec = float(ms[k]) * 1e-3
-                for key in ("wavefront", "wavefront_compact", "open_compact", "neighbors",
-                            "neighbors_compact", "threshold", "goal"):
+                a, s, e, w = (float(v) * 1e-3 for v in ph[k])
+                self.time_data["wavefront"].append(a)
+                self.time_data["neighbors_compact"].append(s)
+                self.time_data["connection"].append(e + w)
+                for key in ("wavefront_compact", "open_compact", "neighbors", "threshold", "goal"):
                     self.time_data[key].append(0.0)
-                self.time_data["connection"].append(sec)
-                self.time_data["elapsed"].append(sec)
+                self.time_data["elapsed"].append(a + s + e + w)
                 self.time_data["iteration"].append(k + 1)

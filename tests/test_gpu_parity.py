@@ -433,3 +433,34 @@ def test_blocked_arrival_masks_do_not_change_results(GMT, oracles, monkeypatch):
     assert np.array_equal(g.dev_cost.view(np.uint32), cost_on.view(np.uint32))
     report("blocked-arrival masks on a 3k world (30 boxes): identical tree with and without; "
            "words tested %d (on) vs %d (off)" % (swept_on, g.last_result.word_checks))
+
+
+def test_route_edges_match_oracle(GMT, oracles):
+    """Trajectory output: winning word and arc / segment / arc lengths of every route edge."""
+    init, it, meta = _world(None, 2000, 20, 19)
+    g = GMT(init)
+    route = list(g.run_step(it, iter_limit=200))
+    assert g.status == 0 and len(route) > 3
+    ft, word, arcs = g.route_edges()
+    oft, oword, oarcs = oracles["cuda"].route_edges(init['states'], route, it['radius'], it['obstacles'], it['num_obs'])
+    assert np.array_equal(ft, oft) and np.array_equal(word, oword)
+    np.testing.assert_allclose(arcs, oarcs, rtol=RTOL, atol=1e-6)
+    cost = g.dev_cost
+    np.testing.assert_allclose(arcs.sum(1), cost[ft[:, 1]] - cost[ft[:, 0]], rtol=1e-4, atol=1e-4)
+    assert ft[0, 0] == it['start'] and ft[-1, 1] == it['goal']
+
+
+def test_time_data_has_the_reference_keys_and_device_phase_times(GMT):
+    """run_step(time=True) fills GMT.time_data like the reference (gmt_planner.py:29,229-239), here with the
+    device time of each phase; test_agent.py:237 turns it into a DataFrame."""
+    import pandas as pd
+    init, it, meta = _world(None, 2000, 20, 19)
+    g = GMT(init)
+    g.run_step(it, iter_limit=200, time=True)
+    keys = {"wavefront", "wavefront_compact", "open_compact", "neighbors", "neighbors_compact", "connection",
+            "elapsed", "threshold", "goal", "iteration"}
+    assert set(g.time_data) == keys
+    df = pd.DataFrame(g.time_data)
+    assert len(df) > 3 and (df["elapsed"] > 0).all() and (df["connection"] > 0).all()
+    assert abs(df["elapsed"].sum() * 1e3 - g.last_result.device_ms) < 0.5 * g.last_result.device_ms
+    assert list(df["iteration"]) == sorted(df["iteration"])
