@@ -26,12 +26,13 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 
 
-def _obstacles(obstacles, num_obs):
-    """Reference convention (cuda_agent.py:201-206): a [[-1,-1,-1,-1]] placeholder with num_obs=[0]."""
+def _obstacles(obstacles, num_obs, width=4):
+    """Reference convention (cuda_agent.py:201-206): a [[-1,-1,-1,-1]] placeholder with num_obs=[0].
+    width 6 = extension-mode oriented rectangles [cx, cy, half_x, half_y, cos_a, sin_a]."""
     m = int(np.asarray(num_obs).reshape(-1)[0]) if num_obs is not None else len(obstacles)
-    obs = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float32).reshape(-1, 4))
+    obs = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float32).reshape(-1, width))
     if obs.shape[0] == 0:
-        obs = np.full((1, 4), -1, dtype=np.float32)
+        obs = np.full((1, width), -1, dtype=np.float32)
     return obs, m
 
 
@@ -72,10 +73,23 @@ class OraclePort:
                                       _u32p, _f32p]
         L.gmto_get_path.restype = C.c_int
         L.gmto_get_path.argtypes = [_i32p, C.c_int, C.c_int, _i32p, C.c_int]
+        L.gmto_set_extensions.restype = None
+        L.gmto_set_extensions.argtypes = [C.c_int, C.c_int]
+        self.words, self.oriented = 4, False
+
+    def set_extensions(self, words=4, oriented=False):
+        """Extension mode (parity unpinned, see gmt_oracle.c): 6 words and / or oriented rectangles
+        given as rows [cx, cy, half_x, half_y, cos_a, sin_a].  (4, False) = reference-parity mode."""
+        self.words, self.oriented = (6 if int(words) == 6 else 4), bool(oriented)
+        self.lib.gmto_set_extensions(self.words, int(self.oriented))
+        return self
+
+    def _obs(self, obstacles, num_obs):
+        return _obstacles(obstacles, num_obs, 6 if self.oriented else 4)
 
     # ---- single word: flags, cost, 150 sample points -------------------------------------
     def word(self, word, start, end, r_min, obstacles=None, num_obs=0):
-        obs, m = _obstacles(obstacles if obstacles is not None else [], [num_obs])
+        obs, m = self._obs(obstacles if obstacles is not None else [], [num_obs])
         cost = C.c_float()
         xs = np.zeros(150, np.float32)
         ys = np.zeros(150, np.float32)
@@ -86,13 +100,13 @@ class OraclePort:
 
     def route_edges(self, states, route, radius, obstacles, num_obs):
         """Trajectory of a goal-first route, start -> goal: (from_to, word, arcs3) like gmt_get_route_edges."""
-        obs, m = _obstacles(obstacles, num_obs)
+        obs, m = self._obs(obstacles, num_obs)
         states = np.ascontiguousarray(states, np.float32)
         path = list(route)[::-1]
         ft, words, arcs = [], [], []
         for a, b in zip(path[:-1], path[1:]):
             bw, bc, ba = 255, np.inf, [np.nan] * 3
-            for w in range(4):
+            for w in range(self.words):
                 cost = C.c_float()
                 a3 = np.zeros(3, np.float32)
                 fl = self.lib.gmto_word_arcs(w, states[a], states[b], int(radius), obs, m, C.byref(cost), a3)
@@ -103,11 +117,11 @@ class OraclePort:
                 np.array(arcs, np.float32).reshape(-1, 3))
 
     def edge_costs(self, states, y, x, radius, obstacles, num_obs):
-        obs, m = _obstacles(obstacles, num_obs)
+        obs, m = self._obs(obstacles, num_obs)
         states = np.ascontiguousarray(states, np.float32)
         y = np.ascontiguousarray(y, np.int32)
         x = np.ascontiguousarray(x, np.int32)
-        cost4 = np.zeros((len(y), 4), np.float32)
+        cost4 = np.zeros((len(y), self.words), np.float32)
         bits = np.zeros(len(y), np.uint32)
         best = np.zeros(len(y), np.float32)
         self.lib.gmto_edge_costs(states, y, x, len(y), float(radius), obs, m, cost4, bits, best)
@@ -119,7 +133,7 @@ class OraclePort:
         states = np.ascontiguousarray(states, np.float32)
         neighbors = np.ascontiguousarray(neighbors, np.int32)
         num_neighbors = np.ascontiguousarray(num_neighbors, np.int32)
-        obs, m = _obstacles(obstacles, num_obs)
+        obs, m = self._obs(obstacles, num_obs)
         n = states.shape[0]
         cost = np.zeros(n, np.float32)
         parent = np.zeros(n, np.int32)

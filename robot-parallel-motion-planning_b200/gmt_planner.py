@@ -11,6 +11,7 @@ CUDA kernel for sm_100a behind the C ABI of include/gmt_c_api.h (ctypes, no PyCu
 fallback: importing this module without the built library raises).
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -22,17 +23,32 @@ except ImportError:  # imported as a top-level module, the way the reference's c
 __all__ = ["GMT"]
 
 
+def oriented_records(rects):
+    """Extension mode: rows [centre_x, centre_y, half_x, half_y, angle_rad] -> the float32 records
+    [cx, cy, half_x, half_y, cos_a, sin_a] that gmt_set_obstacles_oriented takes (cos / sin from libm
+    in double, rounded once)."""
+    r = np.asarray(rects, dtype=np.float64).reshape(-1, 5)
+    out = np.zeros((r.shape[0], 6), np.float32)
+    out[:, :4] = r[:, :4]
+    out[:, 4] = [math.cos(a) for a in r[:, 4]]
+    out[:, 5] = [math.sin(a) for a in r[:, 4]]
+    return out
+
+
 class GMT(object):
     """GMT* planner over a fixed Dubins roadmap (reference: carla/gmt_planner.py:22-239)."""
 
     # the reference prints its exit reason (gmt_planner.py:144,151); set True to get the same lines
     verbose = False
 
-    def __init__(self, init_parameters, debug=False, device=0):
+    def __init__(self, init_parameters, debug=False, device=0, words=4):
         self._lib = _lib.load()
         self._handle = C.c_void_p()
         self._cpu_init(init_parameters, debug)
         self._gpu_init(debug, device)
+        self.words = 4
+        if words != 4:
+            self.set_words(words)
 
         self.route = []
         self.start = 0
@@ -69,6 +85,12 @@ class GMT(object):
         rc = self._lib.gmt_create(states.ctypes.data, self.n, nbr.ctypes.data if nbr.size else None,
                                   cnt.ctypes.data, int(device), C.byref(self._handle))
         _lib.check(rc, "gmt_create")
+
+    def set_words(self, words):
+        """Extension mode (not in the reference, which tries RSR, LSL, LSR, RSL: kernel.py:421-424):
+        words=6 also tries the CCC words RLR and LRL in every later plan; words=4 restores parity mode."""
+        _lib.check(self._lib.gmt_set_words(self._handle, int(words)), "gmt_set_words")
+        self.words = int(words)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -140,16 +162,27 @@ class GMT(object):
     def run_step(self, iter_parameters, iter_limit=1000, debug=False, time=False):
         self.step_init(iter_parameters, debug)
         num_obs = int(np.asarray(self.num_obs).reshape(-1)[0])
-        obs = np.ascontiguousarray(self.obstacles, dtype=np.float32).reshape(-1, 4)
+        # extension (not in the reference): iter_parameters['obstacle_format'] = 'oriented' -> rows
+        # [centre_x, centre_y, half_x, half_y, angle_rad]; default: the reference's [xa, ya, xb, yb]
+        oriented = iter_parameters.get('obstacle_format', 'corners') == 'oriented'
+        obs = np.ascontiguousarray(self.obstacles, dtype=np.float32).reshape(-1, 5 if oriented else 4)
         if num_obs > obs.shape[0]:
             raise ValueError("num_obs exceeds the obstacle array")
         want_trace = bool(debug or time)
         _lib.check(self._lib.gmt_set_trace(self._handle, 1 if want_trace else 0), "gmt_set_trace")
         res = _lib.GmtResult()
-        rc = self._lib.gmt_plan(self._handle, int(self.start), int(self.goal),
-                                float(np.float32(self.radius)), float(self.threshold[0]),
-                                obs.ctypes.data if num_obs > 0 else None, num_obs, int(iter_limit),
-                                C.byref(res))
+        if oriented:
+            rec = oriented_records(obs[:num_obs])
+            _lib.check(self._lib.gmt_set_obstacles_oriented(self._handle, rec.ctypes.data if num_obs > 0 else None,
+                                                            num_obs), "gmt_set_obstacles_oriented")
+            rc = self._lib.gmt_plan_resident(self._handle, int(self.start), int(self.goal),
+                                             float(np.float32(self.radius)), float(self.threshold[0]),
+                                             int(iter_limit), C.byref(res))
+        else:
+            rc = self._lib.gmt_plan(self._handle, int(self.start), int(self.goal),
+                                    float(np.float32(self.radius)), float(self.threshold[0]),
+                                    obs.ctypes.data if num_obs > 0 else None, num_obs, int(iter_limit),
+                                    C.byref(res))
         _lib.check(rc, "gmt_plan")
         self.last_result = res
         self.iterations = res.iterations
