@@ -50,6 +50,10 @@ PROTOTYPES = {
     "gmt_sharded_step": (_i, [_vp, _ip]),
     "gmt_best_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(C.c_longlong)]),
     "gmt_sharded_finish": (_i, [_vp, C.POINTER(GmtResult)]),
+    "gmt_peer_export": (_i, [_vp, _vp]),
+    "gmt_peer_open": (_i, [_vp, _i, _i, _vp]),
+    "gmt_peer_close": (_i, [_vp]),
+    "gmt_plan_sharded_p2p": (_i, [_vp, _i, _i, _f, _f, _i, _i, _i, C.POINTER(GmtResult)]),
     "gmt_measure_fp32_peak": (_i, [_i, _fp]),
     "gmt_last_error": (C.c_char_p, []),
     "gmt_version": (_i, []),

@@ -120,6 +120,60 @@ def run_step_sharded(gmt, iter_parameters, iter_limit=1000, rank=0, world=1, exc
     return gmt.route, res, steps
 
 
+def open_peers(gmt, rank, world):
+    """Maps every rank's cost/parent array and flag block into this rank's address space (CUDA IPC handles
+    swapped with torch.distributed.all_gather_object; NVLink peer access) for run_step_sharded_p2p."""
+    import ctypes as C
+
+    import torch.distributed as dist
+    try:
+        from . import _lib
+    except ImportError:
+        import _lib
+    blob = (C.c_ubyte * 128)()
+    _lib.check(gmt._lib.gmt_peer_export(gmt._handle, blob), "gmt_peer_export")
+    blobs = [None] * world
+    if world > 1:
+        dist.all_gather_object(blobs, bytes(blob))
+    else:
+        blobs = [bytes(blob)]
+    packed = (C.c_ubyte * (128 * world)).from_buffer_copy(b"".join(blobs))
+    _lib.check(gmt._lib.gmt_peer_open(gmt._handle, int(rank), int(world), packed), "gmt_peer_open")
+    if world > 1:
+        dist.barrier()          # nobody plans before everybody has mapped everybody
+
+
+def close_peers(gmt):
+    gmt._lib.gmt_peer_close(gmt._handle)
+
+
+def run_step_sharded_p2p(gmt, iter_parameters, iter_limit=1000, rank=0, world=1):
+    """The sharded plan as ONE kernel launch per GPU: the per-wavefront exchange of the packed cost/parent keys
+    goes over NVLink peer memory inside the kernel (gmt_plan_sharded_p2p; open_peers first).  Every rank must
+    call this with the same query.  Returns (route, gmt_result)."""
+    import ctypes as C
+
+    try:
+        from . import _lib
+    except ImportError:
+        import _lib
+    lib = gmt._lib
+    gmt.step_init(iter_parameters, False)
+    num_obs = int(np.asarray(iter_parameters['num_obs']).reshape(-1)[0])
+    obs = np.ascontiguousarray(iter_parameters['obstacles'], dtype=np.float32).reshape(-1, 4)
+    _lib.check(lib.gmt_set_obstacles(gmt._handle, obs.ctypes.data if num_obs > 0 else None, num_obs), "gmt_set_obstacles")
+    lo, hi = shard_range(gmt.n, rank, world)
+    res = _lib.GmtResult()
+    _lib.check(lib.gmt_plan_sharded_p2p(gmt._handle, int(gmt.start), int(gmt.goal), float(np.float32(gmt.radius)),
+                                        float(gmt.threshold[0]), int(iter_limit), lo, hi, C.byref(res)),
+               "gmt_plan_sharded_p2p")
+    gmt.last_result, gmt.iterations, gmt.status = res, res.iterations, res.status
+    if res.status == _lib.GMT_STATUS_GOAL or res.route_len >= 0:
+        gmt.route = []
+        gmt.get_path()
+    return gmt.route, res
+
+
 def run_step_sharded_emulated(gmts, iter_parameters, iter_limit=1000):
     """The same protocol with all ranks emulated in ONE process on ONE GPU (len(gmts) handles on the same
     roadmap): used by the GPU tests, where more ranks than GPUs must not spin on each other."""

@@ -35,6 +35,25 @@ for rep in range(3):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 same = (list(route) == single) and np.array_equal(g.parent, parent) and np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
+# fused form: one launch per GPU, exchange over NVLink peer memory inside the kernel
+multi_gpu.open_peers(g, rank, world)
+for rep in range(3):
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    route2, res2 = multi_gpu.run_step_sharded_p2p(g, it, iter_limit=1000, rank=rank, world=world)
+    torch.cuda.synchronize()
+    dt2 = time.perf_counter() - t0
+same2 = (list(route2) == single) and np.array_equal(g.parent, parent) and np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
+multi_gpu.close_peers(g)
+flags = torch.tensor([int(same), int(same2)], device="cuda")
+if world > 1:
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+dev2 = multi_gpu.max_over_ranks([res2.device_ms], device="cuda")[0]
+if rank == 0:
+    print("  fused peer-memory exchange: %.3f ms wall, %.3f ms on device (max over ranks), %d wavefronts; identical tree on every rank: %s (NCCL path: %s)"
+          % (dt2 * 1e3, dev2, res2.iterations, bool(flags[1].item()), bool(flags[0].item())))
 if rank == 0:
     print("n=%d m=%d world=%d: single persistent plan %.3f ms (%d wavefronts, %d edge checks); sharded %d launches in %.3f ms wall; identical tree: %s"
           % (n, m, world, t_single, res1.iterations, res1.edge_pairs, steps, dt * 1e3, same))
