@@ -464,3 +464,36 @@ def test_time_data_has_the_reference_keys_and_device_phase_times(GMT):
     assert len(df) > 3 and (df["elapsed"] > 0).all() and (df["connection"] > 0).all()
     assert abs(df["elapsed"].sum() * 1e3 - g.last_result.device_ms) < 0.5 * g.last_result.device_ms
     assert list(df["iteration"]) == sorted(df["iteration"])
+
+
+def test_fused_sharded_plan_with_a_single_rank_equals_plan(GMT):
+    """gmt_plan_sharded_p2p with world = 1 (no peers mapped, the exchange degenerates to grid barriers): the
+    code path of the fused multi-GPU plan that a one-GPU box can exercise."""
+    import multi_gpu
+    init, it, meta = _world(None, 3000, 30, 61)
+    ref = GMT(init)
+    route = list(ref.run_step(it, iter_limit=300))
+    g = GMT(init)
+    multi_gpu.open_peers(g, 0, 1)
+    for _ in range(2):                                   # twice: the flag generations keep growing across plans
+        r, res = multi_gpu.run_step_sharded_p2p(g, it, iter_limit=300, rank=0, world=1)
+        assert list(r) == route and (res.status, res.iterations) == (ref.status, ref.iterations)
+        assert np.array_equal(g.parent, ref.parent)
+        assert np.array_equal(g.dev_cost.view(np.uint32), ref.dev_cost.view(np.uint32))
+    multi_gpu.close_peers(g)
+
+
+def test_fused_sharded_plan_on_two_gpus():
+    """Two ranks under torchrun (one process per GPU): NCCL all-reduce(min) path and the fused NVLink
+    peer-memory path must both rebuild the single-GPU tree on every rank.  Needs >= 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "sharded_check.py"), "30000", "300"]
+    out = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280).stdout
+    assert "identical tree on every rank: True (NCCL path: True)" in out, out[-2000:]
+    report("2 GPUs, 30k nodes: " + [l for l in out.splitlines() if "fused peer-memory" in l][0].strip())
