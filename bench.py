@@ -42,7 +42,9 @@ UNIT = "plans/s"
 WORKLOADS = {4: "cfg4: batch of 4096 independent start/goal queries on a 10k-sample map, sharded by rank, no collective",
              1: "cfg1: single query, 2k samples, 20 obstacles",
              2: "cfg2: single query, 10k samples, 100 obstacles",
-             3: "cfg3: single query, 100k samples, road lattice, 2k obstacles"}
+             3: "cfg3: single query, 100k samples, road lattice, 2k obstacles",
+             5: "cfg5: single query on ONE 1M-sample roadmap (2k obstacles), edge evaluation sharded by node range "
+                "over the GPUs, per-wavefront exchange of the packed cost/parent keys"}
 
 
 def f_edge(m):
@@ -471,6 +473,123 @@ def run_b200_batch(args):
     return 0
 
 
+def run_b200_sharded(args):
+    """BASELINE config 5: ONE plan on a 1M-sample roadmap, every GPU connects the candidate nodes of its node
+    range.  N = 1: the plain persistent plan.  N > 1: the fused form (one launch per GPU, the per-wavefront
+    exchange goes over NVLink peer memory inside the kernel); the NCCL all-reduce(min) form is timed beside it.
+    Strong scaling: value = plans/s of the one plan all GPUs work on."""
+    import ctypes as C
+
+    import torch
+    import _lib
+    import multi_gpu
+    import synthetic_world as sw
+    from gmt_planner import GMT
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the planner has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    init, it, meta = sw.make_world(5, sampler=lambda *a: sw.cuda_sampler(*a, device=local),
+                                   neighbor_builder=lambda s_, r_: sw.cuda_neighbor_builder(s_, r_, device=local))
+    n, m = meta["n"], meta["m"]
+    cached = workload_meta(5)
+    if cached.get("n") == n and cached.get("seed") == meta["seed"] and cached.get("start") == int(it['start']):
+        goal = int(cached["goal"])
+    else:
+        goal = sw.pick_reachable_goal(init, it, meta["side"], explore=lambda a, b: sw.explore_cuda(a, b, device=local)) \
+            if rank == 0 else 0
+        gt = torch.tensor([goal], device=dev)
+        if dist is not None:
+            dist.broadcast(gt, 0)
+        goal = int(gt.item())
+    it = dict(it, goal=goal)
+    g = GMT(init, device=local)
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(lib.gmt_set_stream(g._handle, C.c_void_p(stream.cuda_stream)), "gmt_set_stream")
+    single = list(g.run_step(it, iter_limit=1000))                   # also the check value for the sharded forms
+    res1 = g.last_result
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    if world > 1:
+        multi_gpu.open_peers(g, rank, world)
+
+        def step():
+            return multi_gpu.run_step_sharded_p2p(g, it, iter_limit=1000, rank=rank, world=world)
+    else:
+        def step():
+            return g.run_step(it, iter_limit=1000), g.last_result
+    for _ in range(max(args.warmup, 3)):
+        route, res = step()
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches = 0
+    barrier()
+    for k in range(K):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        route, res = step()
+        ev[k][1].record(stream)
+        launches += res.launches
+    barrier()
+    t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    same = int(list(route) == single)
+    nccl_ms = None
+    if world > 1:
+        multi_gpu.close_peers(g)
+        barrier()
+        t0 = time.perf_counter()
+        r2, _res2, steps2 = multi_gpu.run_step_sharded(g, it, iter_limit=1000, rank=rank, world=world)
+        torch.cuda.synchronize(dev)
+        nccl_ms = (time.perf_counter() - t0) * 1e3
+        same = int(same and list(r2) == single)
+    t, nccl_ms_max = multi_gpu.max_over_ranks([t, nccl_ms or 0.0], device=dev)
+    flags = torch.tensor([same], device=dev)
+    if dist is not None:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        value = K / t
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": max(args.warmup, 3), "ms_per_step": t / K * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS[5], "n": n, "m": m, "seed": meta["seed"],
+                           "l2": "flushed between timed plans (256 MiB fill)",
+                           "exchange": "none (one GPU)" if world == 1 else
+                                       "in-kernel stores into the peers' arrays over NVLink + flag barrier in peer memory",
+                           "plan": {"status": res1.status, "wavefronts": res1.iterations, "edge_checks": res1.edge_pairs,
+                                    "route_len": len(single), "single_gpu_ms": res1.device_ms},
+                           "identical_tree_on_every_rank": bool(flags.item()),
+                           "nccl_allreduce_min_path_ms": nccl_ms_max if world > 1 else None},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(16 * m),
+                        "d2h_bytes_per_step": int(512 + 4 * min(n + 1, 1024)),
+                        "note": "timed through GMT.run_step / multi_gpu.run_step_sharded_p2p with host obstacle arrays"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "unit": "TFLOP/s", "traffic": None,
+                             "achieved": res1.edge_pairs * f_edge(m) / (t / K) * 1e-12, "peak": None, "frac": None}}
+        print(json.dumps(line), flush=True)
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "workload_cfg5.json"), "w") as f:
+                json.dump({"n": n, "m": m, "seed": meta["seed"], "start": int(it['start']), "goal": goal,
+                           "edge_pairs": res1.edge_pairs, "wavefronts": res1.iterations, "status": res1.status}, f)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -482,13 +601,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.config == 4:
+        if args.config in (4, 5):
             args.config = 2          # the CPU arm times one query of the same kind of map
         return run_reference(args)
     if args.config == 4:
         if args.steps == 200:
             args.steps = 5
         return run_b200_batch(args)
+    if args.config == 5:
+        if args.steps == 200:
+            args.steps = 10
+        return run_b200_sharded(args)
     return run_b200(args)
 
 

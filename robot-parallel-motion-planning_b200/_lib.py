@@ -45,6 +45,8 @@ PROTOTYPES = {
     "gmt_build_neighbors": (_i, [_vp, _i, C.c_double, _i, C.POINTER(_vp), C.POINTER(_vp),
                                  C.POINTER(C.c_longlong)]),
     "gmt_free": (None, [_vp]),
+    "gmt_insert_states": (_i, [_vp, _vp, _i, C.c_double, _ip]),
+    "gmt_reset_inserted": (_i, [_vp]),
     "gmt_plan_batch": (_i, [_vp, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _i]),
     "gmt_sharded_begin": (_i, [_vp, _i, _i, _f, _f, _i, _i, _i]),
     "gmt_sharded_step": (_i, [_vp, _ip]),

@@ -92,6 +92,28 @@ class GMT(object):
         _lib.check(self._lib.gmt_set_words(self._handle, int(words)), "gmt_set_words")
         self.words = int(words)
 
+    def insert_states(self, states_xyt, disk_radius=4 * math.sqrt(2)):
+        """Extension: append states (e.g. the vehicle's current pose as a new start) to the resident
+        roadmap without rebuilding the neighbour lists; returns their ids.  The reference rebuilds the whole
+        roadmap with start and goal appended (cuda_agent.py:64-66).  Plans equal plans on the rebuilt roadmap."""
+        new = np.ascontiguousarray(states_xyt, dtype=np.float32).reshape(-1, 3)
+        first = C.c_int()
+        _lib.check(self._lib.gmt_insert_states(self._handle, new.ctypes.data, new.shape[0], float(disk_radius),
+                                               C.byref(first)), "gmt_insert_states")
+        self.states = np.concatenate([np.asarray(self.states, np.float32).reshape(-1, 3), new], 0)
+        self.n = self.states.shape[0]
+        self.waypoints = np.arange(self.n).astype(np.int32)
+        self._parent = self._cost = None
+        return list(range(first.value, first.value + new.shape[0]))
+
+    def reset_inserted(self):
+        """Drops every state appended by insert_states."""
+        _lib.check(self._lib.gmt_reset_inserted(self._handle), "gmt_reset_inserted")
+        self.n = int(np.asarray(self.num_neighbors).shape[0])
+        self.states = np.asarray(self.states).reshape(-1, 3)[:self.n]
+        self.waypoints = np.arange(self.n).astype(np.int32)
+        self._parent = self._cost = None
+
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and h.value:

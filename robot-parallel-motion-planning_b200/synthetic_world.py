@@ -211,3 +211,49 @@ def make_reachable_queries(gmt, n, q, seed, radius=2.0, threshold=1.0, iter_limi
     goals = np.array([r.farthest_frontier if r.farthest_frontier >= 0 else int(s) for r, s in zip(res, starts)],
                      np.int32)
     return starts, goals
+
+
+# ------------------------------------------------------------------------------------------------------
+# Obstacle ingestion (reference: CudaAgent._trace_route, cuda_agent.py:127-206)
+# ------------------------------------------------------------------------------------------------------
+def vehicles_to_obstacles(vehicles, ego_xy, margin=2.5, max_dist=30.0, oriented=False):
+    """Vehicle boxes -> the planner's obstacle array, the way the reference builds it every re-plan.
+
+    vehicles: rows [x, y, yaw_deg, extent_x, extent_y, box_offset_x, box_offset_y] (vehicle pose, half
+    extents and centre offset of its bounding box in the vehicle frame: what CARLA's actor transform and
+    bounding_box give; planar world, so pitch = roll = 0 and z plays no role).  ego_xy: centre of the ego
+    vehicle's box.  Kept like the reference (cuda_agent.py:186-198):
+      * the two diagonal corners (+-(extent + 2.5 m)) of the inflated box are taken to the world frame and
+        used AS the two opposite corners [xa, ya, xb, yb] of an axis-aligned box -- for a turned vehicle
+        that is not the bounding box of the rotated rectangle (at 45 degrees it degenerates to a sliver);
+      * only vehicles whose box centre is within 0 < d <= 30 m of the ego's are obstacles (which also drops
+        the ego itself);
+      * no obstacle -> the placeholder [[-1, -1, -1, -1]] with num_obs = [0].
+    oriented=True (extension, not in the reference) returns instead the geometrically faithful inflated
+    rectangles as rows [centre_x, centre_y, half_x, half_y, angle_rad] for
+    iter_parameters['obstacle_format'] = 'oriented'.
+    Returns (obstacles float32[m, 4 or 5], num_obs int32[1])."""
+    v = np.asarray(vehicles, dtype=np.float64).reshape(-1, 7)
+    ego = np.asarray(ego_xy, dtype=np.float64).reshape(2)
+    yaw = np.radians(v[:, 2])
+    c, s = np.cos(yaw), np.sin(yaw)
+
+    def to_world(px, py):          # bounding-box frame -> vehicle frame (offset) -> world (yaw, position)
+        lx, ly = v[:, 5] + px, v[:, 6] + py
+        return v[:, 0] + c * lx - s * ly, v[:, 1] + s * lx + c * ly
+
+    ex, ey = v[:, 3] + margin, v[:, 4] + margin
+    xa, ya = to_world(ex, ey)
+    xb, yb = to_world(-ex, -ey)
+    cx, cy = to_world(np.zeros(len(v)), np.zeros(len(v)))
+    d = np.hypot(cx - ego[0], cy - ego[1])
+    near = (d > 0) & (d <= max_dist)
+    m = int(near.sum())
+    if m == 0:
+        width = 5 if oriented else 4
+        return np.full((1, width), -1, np.float32), np.array([0], np.int32)
+    if oriented:
+        obs = np.stack([cx, cy, ex, ey, yaw], 1)[near]
+    else:
+        obs = np.stack([xa, ya, xb, yb], 1)[near]
+    return obs.astype(np.float32), np.array([m], np.int32)

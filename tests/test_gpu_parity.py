@@ -497,3 +497,52 @@ def test_fused_sharded_plan_on_two_gpus():
     out = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280).stdout
     assert "identical tree on every rank: True (NCCL path: True)" in out, out[-2000:]
     report("2 GPUs, 30k nodes: " + [l for l in out.splitlines() if "fused peer-memory" in l][0].strip())
+
+
+def test_appended_states_equal_the_rebuilt_roadmap(GMT, oracles):
+    """a new start pose and a new goal appended to the resident roadmap (no CSR rebuild) must plan
+    exactly like the roadmap rebuilt from scratch with those two states at the end (what the reference does,
+    cuda_agent.py:64-66,114-117) -- and like the CPU oracle on that rebuilt roadmap."""
+    import synthetic_world as sw
+    init, it, meta = _world(None, 2000, 20, 19)
+    S = meta["side"]
+    base_route = list(GMT(init).run_step(it, iter_limit=200))
+    assert len(base_route) > 6
+    mid = init['states'][base_route[len(base_route) // 3]]          # a pose the wavefront does reach
+    s0 = init['states'][it['start']]
+    new = np.array([[s0[0] + 0.4, s0[1] - 0.3, s0[2] + 0.1], [mid[0] + 0.3, mid[1] + 0.2, mid[2] + 0.05],
+                    [s0[0] + 0.4, s0[1] - 0.3, s0[2] - 0.4]], np.float32)
+    # rebuilt: all states + the three new ones, neighbour lists from scratch
+    states2 = np.concatenate([init['states'], new], 0)
+    nbr2, num2 = sw.cuda_neighbor_builder(states2)
+    init2 = dict(init, states=states2, neighbors=nbr2, num_neighbors=num2)
+    n0 = init['states'].shape[0]
+    q = dict(it, start=n0, goal=n0 + 1)
+    g2 = GMT(init2)
+    route2 = list(g2.run_step(q, iter_limit=200, debug=True))
+    # incremental: first two states in one call, the third (same location as the first: never its neighbour) later
+    g1 = GMT(init)
+    assert list(g1.run_step(it, iter_limit=200)) == base_route
+    ids = g1.insert_states(new[:2]) + g1.insert_states(new[2:])
+    assert ids == [n0, n0 + 1, n0 + 2] and g1.n == n0 + 3
+    route1 = list(g1.run_step(q, iter_limit=200, debug=True))
+    assert route1 == route2 and g1.status == g2.status and g1.iterations == g2.iterations
+    assert g1.status == 0 and route1[0] == n0 + 1 and route1[-1] == n0
+    assert np.array_equal(g1.parent, g2.parent)
+    assert np.array_equal(g1.dev_cost.view(np.uint32), g2.dev_cost.view(np.uint32))
+    for a, b in zip(g1.trace, g2.trace):
+        assert (a["gSize"], a["ySize"], a["xSize"]) == (b["gSize"], b["ySize"], b["xSize"])
+    r = oracles["cuda"].plan(states2, nbr2, num2, n0, n0 + 1, q['radius'], q['threshold'], q['obstacles'], q['num_obs'],
+                             iter_limit=200)
+    _compare_plan(g1, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], states2, "appended states")
+    # a plan that ends AT an appended state reached through old nodes, and one that starts from the third
+    assert list(g1.run_step(dict(it, goal=n0 + 1), iter_limit=200)) == list(g2.run_step(dict(it, goal=n0 + 1), iter_limit=200))
+    assert list(g1.run_step(dict(q, start=n0 + 2), iter_limit=200)) == list(g2.run_step(dict(q, start=n0 + 2), iter_limit=200))
+    # dropping them gives the base roadmap back
+    g1.reset_inserted()
+    assert g1.n == n0 and list(g1.run_step(it, iter_limit=200)) == base_route
+    import _lib
+    with pytest.raises(_lib.GmtError):
+        g1.insert_states(np.zeros((17, 3), np.float32))
+    report("appended states (2000-node roadmap + 3 poses, no CSR rebuild): route, parents and cost bits identical to "
+           "the rebuilt roadmap; %d nodes connected" % int((g2.parent >= 0).sum()))
