@@ -124,6 +124,11 @@ class ClockSampler:
         return out
 
 
+def gpu_uuid(torch, dev, local):
+    props = torch.cuda.get_device_properties(dev)
+    return "GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local)
+
+
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU implementation on a bounded sample
 # --------------------------------------------------------------------------------------------------
@@ -270,9 +275,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    props = torch.cuda.get_device_properties(dev)
-    gpu_id = "GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local)
-    sampler = ClockSampler(gpu_id)
+    sampler = ClockSampler(gpu_uuid(torch, dev, local))
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         plan_resident()
@@ -434,8 +437,11 @@ def run_b200_batch(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(gpu_uuid(torch, dev, local))
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         res, _r = sw.plan_batch(g, s, gl)
+    sampler.mark()
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches, kern_ms = 0, 0.0
@@ -449,6 +455,7 @@ def run_b200_batch(args):
         kern_ms += res[0].device_ms
     barrier()
     t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    clocks = sampler.stop()
     (t,) = multi_gpu.max_over_ranks([t], device=dev)
     reached = sum(r.status == 0 for r in res)
     pairs = sum(r.edge_pairs for r in res)
@@ -464,6 +471,8 @@ def run_b200_batch(args):
                         "d2h_bytes_per_step": int(len(s) * (136 + 4 * 128)),
                         "note": "the batch call takes host start/goal arrays and returns host results + routes: value is e2e"},
                 "gpu_launches": launches,
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                           "samples": clocks["samples"]},
                 "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "unit": "TFLOP/s", "traffic": None,
                              "achieved": pairs * f_edge(m) / (kern_ms / K * 1e-3) * 1e-12, "peak": None, "frac": None,
                              "kernel_ms": kern_ms / K}}
@@ -532,8 +541,11 @@ def run_b200_sharded(args):
     else:
         def step():
             return g.run_step(it, iter_limit=1000), g.last_result
+    sampler = ClockSampler(gpu_uuid(torch, dev, local))
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         route, res = step()
+    sampler.mark()
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches = 0
@@ -546,6 +558,7 @@ def run_b200_sharded(args):
         launches += res.launches
     barrier()
     t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    clocks = sampler.stop()
     same = int(list(route) == single)
     nccl_ms = None
     if world > 1:
@@ -577,8 +590,12 @@ def run_b200_sharded(args):
                         "d2h_bytes_per_step": int(512 + 4 * min(n + 1, 1024)),
                         "note": "timed through GMT.run_step / multi_gpu.run_step_sharded_p2p with host obstacle arrays"},
                 "gpu_launches": launches,
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                           "samples": clocks["samples"]},
                 "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "unit": "TFLOP/s", "traffic": None,
-                             "achieved": res1.edge_pairs * f_edge(m) / (t / K) * 1e-12, "peak": None, "frac": None}}
+                             "achieved": res1.edge_pairs * f_edge(m) / (t / K) * 1e-12, "peak": None, "frac": None,
+                             "note": "algorithmic op count of the reference formulation (SURVEY 8d); exact pruning "
+                                     "skips almost all of it, see profiles/ for the issue-slot utilisation"}}
         print(json.dumps(line), flush=True)
         out_dir = os.path.join(ROOT, "gpurun_out")
         if os.path.isdir(out_dir):
