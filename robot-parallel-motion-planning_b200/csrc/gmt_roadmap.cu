@@ -166,37 +166,72 @@ __device__ __forceinline__ bool is_neighbour(float xi, float yi, float4 c, doubl
     return (double)d <= r;                                        // inclusive (cuda_agent.py:80)
 }
 
-// pass 0: count row lengths; pass 1: write + sort rows.  One thread per state; the members of a
-// cell are contiguous float4 records, so a warp working on neighbouring states streams them.
+// pass 0: count row lengths; pass 1: write the rows, ascending.  One WARP per state, states taken in cell order
+// (neighbouring warps scan the same 3 x 3 cells: L1/L2 hits); the members of a cell row are contiguous float4
+// records, so the 32 lanes stream them coalesced and test 32 candidates at once.  Pass 1 compacts the row into
+// shared memory by ballot, rank-sorts it there (ids are distinct: rank = number of smaller ids) and writes it
+// out in order.  Rows longer than ROW_SMEM fall back to repeated warp-wide minimum selection (slow, never seen
+// on the BASELINE maps where rows hold ~55 entries).
+#define NBR_WARPS 8
+#define ROW_SMEM 256
 template <int kPass>
-__global__ void neighbour_kernel(const float *__restrict__ xyt, int n, CellGrid g, double r,
+__global__ void __launch_bounds__(NBR_WARPS * 32) neighbour_kernel(int n, CellGrid g, double r,
                                  const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                  int *row_cnt_or_off, int *vals)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float xi = xyt[3 * i], yi = xyt[3 * i + 1];
+    __shared__ int s_row[kPass ? NBR_WARPS : 1][kPass ? ROW_SMEM : 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int s = blockIdx.x * NBR_WARPS + wib;
+    if (s >= n) return;
+    const float4 me = sorted[s];
+    const float xi = me.x, yi = me.y;
+    const int i = __float_as_int(me.z);
     int cx, cy;
     cell_of(g, xi, yi, cx, cy);
     int cnt = 0;
-    int *row = kPass ? vals + row_cnt_or_off[i] : nullptr;
     for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); yy++) {
         const int ca = yy * g.nx + max(cx - 1, 0), cb = yy * g.nx + min(cx + 1, g.nx - 1);
         const int e = cell_start[cb + 1];
-        for (int k = cell_start[ca]; k < e; k++) {                // three cells of a row are contiguous
-            const float4 c = sorted[k];
-            if (is_neighbour(xi, yi, c, r)) {
-                if (kPass) row[cnt] = __float_as_int(c.z);
-                cnt++;
+        for (int kb = cell_start[ca]; kb < e; kb += 32) {         // three cells of a row are contiguous
+            const int k = kb + lane;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool hit = false;
+            if (k < e) { c = sorted[k]; hit = is_neighbour(xi, yi, c, r); }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (kPass && hit) {
+                const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                if (pos < ROW_SMEM) s_row[wib][pos] = __float_as_int(c.z);
             }
+            cnt += __popc(m);
         }
     }
-    if (!kPass) { row_cnt_or_off[i] = cnt; return; }
-    for (int a = 1; a < cnt; a++) {                               // insertion sort, rows are short (~56)
-        const int v = row[a];
-        int b = a - 1;
-        while (b >= 0 && row[b] > v) { row[b + 1] = row[b]; b--; }
-        row[b + 1] = v;
+    if (!kPass) { if (lane == 0) row_cnt_or_off[i] = cnt; return; }
+    int *row = vals + row_cnt_or_off[i];
+    __syncwarp();
+    if (cnt <= ROW_SMEM) {
+        for (int a = lane; a < cnt; a += 32) {
+            const int v = s_row[wib][a];
+            int rank = 0;
+            for (int b = 0; b < cnt; b++) rank += s_row[wib][b] < v;      // broadcast reads
+            row[rank] = v;
+        }
+        return;
+    }
+    int last = -1;                                                 // generic fallback: next smallest id, cnt times
+    for (int out = 0; out < cnt; out++) {
+        int best = 0x7fffffff;
+        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); yy++) {
+            const int ca = yy * g.nx + max(cx - 1, 0), cb = yy * g.nx + min(cx + 1, g.nx - 1);
+            const int e = cell_start[cb + 1];
+            for (int k = cell_start[ca] + lane; k < e; k += 32) {
+                const float4 c = sorted[k];
+                const int id = __float_as_int(c.z);
+                if (id > last && id < best && is_neighbour(xi, yi, c, r)) best = id;
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0) row[out] = best;
+        last = best;
     }
 }
 
@@ -268,7 +303,8 @@ int gmt_build_neighbors(const float *states_xyt, int n, double disk_radius, int 
     scan_add_kernel<<<nbc, SCAN_BLOCK>>>(d_start, ncell, d_sums, d_total);
     RCK(cudaMemcpy(d_fill, d_start, sizeof(int) * ((size_t)ncell + 1), cudaMemcpyDeviceToDevice));
     cell_scatter_kernel<<<gb, tb>>>(d_xyt, n, d_cell, d_fill, d_sorted);
-    neighbour_kernel<0><<<gb, tb>>>(d_xyt, n, g, disk_radius, d_start, d_sorted, d_row, nullptr);
+    const int gw = (n + NBR_WARPS - 1) / NBR_WARPS;
+    neighbour_kernel<0><<<gw, NBR_WARPS * 32>>>(n, g, disk_radius, d_start, d_sorted, d_row, nullptr);
     RCK(cudaGetLastError());
 
     int *h_counts = (int *)malloc(sizeof(int) * N);
@@ -281,7 +317,7 @@ int gmt_build_neighbors(const float *states_xyt, int n, double disk_radius, int 
     RCK(cudaMemcpy(&tot, d_total, sizeof(long long), cudaMemcpyDeviceToHost));
     if (tot > 0x7fffffffLL) { free(h_counts); return GMT_ERR_INVALID; }
     RCK(cudaMalloc(&d_vals, sizeof(int) * (size_t)std::max<long long>(tot, 1)));
-    neighbour_kernel<1><<<gb, tb>>>(d_xyt, n, g, disk_radius, d_start, d_sorted, d_row, d_vals);
+    neighbour_kernel<1><<<gw, NBR_WARPS * 32>>>(n, g, disk_radius, d_start, d_sorted, d_row, d_vals);
     RCK(cudaGetLastError());
     int *h_vals = (int *)malloc(sizeof(int) * (size_t)std::max<long long>(tot, 1));
     if (!h_vals) { free(h_counts); return GMT_ERR_NOMEM; }

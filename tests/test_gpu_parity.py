@@ -297,7 +297,8 @@ def test_replanning_on_one_instance(GMT, oracles):
 # ------------------------------------------------------------------------------------------------
 # roadmap builders
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,n,side", [("uniform", 20000, 190.7), ("lattice", 7 * 900, 116.0), ("uniform", 1, 3.0)])
+@pytest.mark.parametrize("mode,n,side", [("uniform", 20000, 190.7), ("lattice", 7 * 900, 116.0), ("uniform", 1, 3.0),
+                                         ("uniform", 700, 5.0)])      # last: rows of ~500 entries (long-row path)
 def test_sampler_and_neighbour_search_bit_exact(gmt_lib, mode, n, side):
     import synthetic_world as sw
     from oracle.world_oracle import build_neighbors, sample_states
