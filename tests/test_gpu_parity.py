@@ -547,3 +547,67 @@ def test_appended_states_equal_the_rebuilt_roadmap(GMT, oracles):
         g1.insert_states(np.zeros((17, 3), np.float32))
     report("appended states (2000-node roadmap + 3 poses, no CSR rebuild): route, parents and cost bits identical to "
            "the rebuilt roadmap; %d nodes connected" % int((g2.parent >= 0).sum()))
+
+
+# ------------------------------------------------------------------------------------------------
+# more corners of the reference's behaviour
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("radius", [0.5, 1.0, 2.9, 3.0])
+def test_turning_radius_is_truncated_like_the_reference(GMT, oracles, radius):
+    """`int r_min` (kernel.py:38): radius 2.9 plans with r = 2, radius 0.5 with r = 0 (arcs collapse to points),
+    while the threshold still grows by 2 * radius (kernel.py:491)."""
+    init, it, meta = _world(None, 1500, 15, 53, reachable=False)
+    it = dict(it, radius=radius)
+    g = GMT(init)
+    g.run_step(dict(it, goal=-1), iter_limit=40)
+    goal = g.last_result.farthest_frontier
+    it = dict(it, goal=int(goal) if goal >= 0 else it['goal'])
+    g.run_step(it, iter_limit=60, debug=True)
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             radius, it['threshold'], it['obstacles'], it['num_obs'], iter_limit=60)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "radius %g" % radius)
+
+
+def test_goal_inside_an_obstacle_returns_the_1e10_route(GMT, oracles):
+    """Every word into a boxed-in goal collides: it is connected at 1e10 (kernel.py:419-427), never enters a
+    wavefront, the plan ends at the iteration limit -- and the reference still returns a route because
+    parent[goal] != -1 (gmt_planner.py:146-148)."""
+    init, it, meta = _world(None, 1200, 0, 57)
+    gs = init['states'][it['goal']]
+    obs = np.array([[gs[0] - 1.0, gs[1] - 1.0, gs[0] + 1.0, gs[1] + 1.0]], np.float32)
+    it = dict(it, obstacles=obs, num_obs=np.array([1], np.int32))
+    g = GMT(init)
+    route = list(g.run_step(it, iter_limit=80, debug=True))
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             it['radius'], it['threshold'], obs, [1], iter_limit=80)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "boxed goal")
+    assert g.status == 1 and route == r["route"]
+    if r["parent"][it['goal']] != -1:
+        assert route[0] == it['goal'] and g.dev_cost[it['goal']] >= 1e10
+
+
+def test_isolated_start_and_growing_obstacle_sets(GMT, oracles):
+    init, it, meta = _world(None, 900, 0, 59)
+    # a start without neighbours: nothing to expand, the reference spins to the limit (gmt_planner.py:156-158)
+    nbr, num = init['neighbors'], init['num_neighbors'].copy()
+    rows = np.repeat(np.arange(len(num)), num)
+    keep = rows != it['start']
+    num2 = np.bincount(rows[keep], minlength=len(num)).astype(np.int32)
+    g = GMT(dict(init, neighbors=nbr[keep].astype(np.int32), num_neighbors=num2))
+    assert g.run_step(it, iter_limit=500) == [] and (g.status, g.iterations) == (1, 500)
+    assert (g.parent == -1).all()
+    # obstacle arrays of very different sizes on one instance (device buffers grow and shrink logically)
+    g = GMT(init)
+    rng = np.random.default_rng(2)
+    S = meta["side"]
+    for m in (3, 700, 0, 64, 2500, 1):
+        c, hh = rng.uniform(0, S, (max(m, 1), 2)), rng.uniform(0.2, 1.0, (max(m, 1), 2))
+        obs = np.concatenate([c - hh, c + hh], 1).astype(np.float32)
+        s0 = init['states'][it['start']]
+        obs = obs[np.hypot(obs[:, 0] + hh[:, 0] - s0[0], obs[:, 1] + hh[:, 1] - s0[1]) > 4.0] if m else obs
+        mm = len(obs) if m else 0
+        q = dict(it, obstacles=obs if mm else np.array([[-1, -1, -1, -1]], np.float32), num_obs=np.array([mm], np.int32))
+        g.run_step(q, iter_limit=40, debug=True)
+        r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                                 it['radius'], it['threshold'], q['obstacles'], q['num_obs'], iter_limit=40)
+        _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "m=%d" % mm)
