@@ -611,3 +611,26 @@ def test_isolated_start_and_growing_obstacle_sets(GMT, oracles):
         r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
                                  it['radius'], it['threshold'], q['obstacles'], q['num_obs'], iter_limit=40)
         _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "m=%d" % mm)
+
+
+@pytest.mark.parametrize("k", [2, 4, 16])
+def test_several_warps_per_candidate_do_not_change_results(GMT, oracles, monkeypatch, k):
+    """Select phase with K warps sharing one candidate node (chosen automatically on large, thin fronts -- sharded
+    plans above all; forced here): same tree as one warp per node, and as the CPU oracle."""
+    init, it, meta = _world(None, 3000, 30, 61)
+    ref = GMT(init)
+    route = list(ref.run_step(it, iter_limit=200))
+    parent, cost = ref.parent.copy(), ref.dev_cost.copy()
+    monkeypatch.setenv("GMT_SELECT_K", str(k))
+    g = GMT(init)
+    assert list(g.run_step(it, iter_limit=200, debug=True)) == route
+    assert np.array_equal(g.parent, parent) and np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=200)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "K=%d" % k)
+    # and in the sharded form (own-candidate list + K warps), ranks emulated in one process
+    import multi_gpu
+    ranks = [GMT(init) for _ in range(2)]
+    out, steps = multi_gpu.run_step_sharded_emulated(ranks, it, iter_limit=200)
+    for gg, (rr, res) in zip(ranks, out):
+        assert rr == route and np.array_equal(gg.parent, parent)
