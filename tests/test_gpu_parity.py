@@ -622,6 +622,7 @@ def test_several_warps_per_candidate_do_not_change_results(GMT, oracles, monkeyp
     route = list(ref.run_step(it, iter_limit=200))
     parent, cost = ref.parent.copy(), ref.dev_cost.copy()
     monkeypatch.setenv("GMT_SELECT_K", str(k))
+    monkeypatch.setenv("GMT_WIDE", "1")          # the plan-kernel instantiation with warp groups (default from 30k nodes)
     g = GMT(init)
     assert list(g.run_step(it, iter_limit=200, debug=True)) == route
     assert np.array_equal(g.parent, parent) and np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
