@@ -468,7 +468,7 @@ def run_b200_batch(args):
                            "queries_per_rank": len(s), "l2": "flushed between timed batches (256 MiB fill)",
                            "goal_reached_rank0": reached, "edge_checks_rank0": pairs},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * len(s)),
-                        "d2h_bytes_per_step": int(len(s) * (136 + 4 * 128)),
+                        "d2h_bytes_per_step": int(len(s) * (144 + 4 * 128)),
                         "note": "the batch call takes host start/goal arrays and returns host results + routes: value is e2e"},
                 "gpu_launches": launches,
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
