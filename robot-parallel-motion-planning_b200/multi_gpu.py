@@ -77,6 +77,23 @@ def best_tensor(gmt):
     return torch.as_tensor(_DeviceArray(ptr.value, count.value, "<i8"), device="cuda")
 
 
+def pack_keys(cost, parent):
+    """The exchange format of the sharded plan as int64: float32 bits of cost (>= 0, +inf = unconnected) in the
+    high word, parent id in the low word (-1 -> 0xFFFFFFFF).  Integer MIN over ranks = lowest cost, ties -> lowest
+    parent id: the reference's strict-less scan over ascending y (kernel.py:427,440-443); an unconnected node
+    loses to any connected one."""
+    c = np.ascontiguousarray(cost, np.float32).view(np.uint32).astype(np.int64)
+    q = np.ascontiguousarray(parent, np.int32).view(np.uint32).astype(np.int64)
+    return (c << 32) | q
+
+
+def unpack_keys(keys):
+    k = np.asarray(keys, np.int64)
+    cost = (k >> 32).astype(np.uint32).view(np.float32)
+    parent = (k & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+    return cost, parent
+
+
 def allreduce_min(t):
     """The per-wavefront exchange: NCCL all-reduce(min) of the packed cost/parent array over NVLink."""
     import torch.distributed as dist
