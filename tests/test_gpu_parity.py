@@ -635,3 +635,22 @@ def test_several_warps_per_candidate_do_not_change_results(GMT, oracles, monkeyp
     out, steps = multi_gpu.run_step_sharded_emulated(ranks, it, iter_limit=200)
     for gg, (rr, res) in zip(ranks, out):
         assert rr == route and np.array_equal(gg.parent, parent)
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_tiny_pair_list_forces_segmented_open_list(GMT, oracles, monkeypatch, wide):
+    """The surviving (x, y) pairs of a wavefront normally fit the pair list; when they cannot, the open list is
+    processed in segments (select + connect per segment, the bound carried in best[x]).  Force that path."""
+    init, it, meta = _world(None, 3000, 30, 61)
+    ref = GMT(init)
+    route = list(ref.run_step(it, iter_limit=200))
+    parent, cost = ref.parent.copy(), ref.dev_cost.copy()
+    monkeypatch.setenv("GMT_PAIR_CAP", "256")
+    monkeypatch.setenv("GMT_WIDE", wide)
+    g = GMT(init)
+    assert list(g.run_step(it, iter_limit=200)) == route
+    assert np.array_equal(g.parent, parent) and np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
+    r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
+                             it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=200)
+    g.run_step(it, iter_limit=200, debug=True)
+    _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "pair_cap 256")
