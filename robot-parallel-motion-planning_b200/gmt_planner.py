@@ -139,11 +139,12 @@ class GMT(object):
 
     def get_path(self):
         """gmt_planner.py:103-107 -- the walk goal -> start happened on the device."""
-        cap = self.n + 1
-        buf = np.zeros(cap, np.int32)
+        res = getattr(self, "last_result", None)
+        cap = (res.route_len if res is not None and res.route_len >= 0 else self.n) + 1   # no n-sized buffer per plan
+        buf = np.empty(cap, np.int32)
         ln = C.c_int()
         _lib.check(self._lib.gmt_get_route(self._handle, buf.ctypes.data, cap, C.byref(ln)), "gmt_get_route")
-        self.route += [int(v) for v in buf[:ln.value]]
+        self.route += buf[:ln.value].tolist()
 
     def route_edges(self):
         """Trajectory of the last route, start -> goal: arrays (from_to int32[E,2], word uint8[E],
