@@ -31,6 +31,7 @@ PROTOTYPES = {
     "gmt_plan": (_i, [_vp, _i, _i, _f, _f, _vp, _i, _i, C.POINTER(GmtResult)]),
     "gmt_set_obstacles": (_i, [_vp, _vp, _i]),
     "gmt_plan_resident": (_i, [_vp, _i, _i, _f, _f, _i, C.POINTER(GmtResult)]),
+    "gmt_update_obstacles": (_i, [_vp, _vp, _vp, _i]),
     "gmt_set_words": (_i, [_vp, _i]),
     "gmt_set_obstacles_oriented": (_i, [_vp, _vp, _i]),
     "gmt_get_route": (_i, [_vp, _vp, _i, _ip]),

@@ -92,6 +92,22 @@ class GMT(object):
         _lib.check(self._lib.gmt_set_words(self._handle, int(words)), "gmt_set_words")
         self.words = int(words)
 
+    def set_obstacles(self, obstacles, num_obs=None):
+        """Extension: make an obstacle set resident on the device; later run_step calls whose
+        iter_parameters['obstacles'] is None plan against it without any upload."""
+        obs = np.ascontiguousarray(obstacles, dtype=np.float32).reshape(-1, 4)
+        m = obs.shape[0] if num_obs is None else int(np.asarray(num_obs).reshape(-1)[0])
+        _lib.check(self._lib.gmt_set_obstacles(self._handle, obs.ctypes.data if m > 0 else None, m), "gmt_set_obstacles")
+
+    def update_obstacles(self, index, obstacles):
+        """Replace the boxes `index` of the resident set in place (only those cross PCIe)."""
+        idx = np.ascontiguousarray(index, dtype=np.int32).reshape(-1)
+        obs = np.ascontiguousarray(obstacles, dtype=np.float32).reshape(-1, 4)
+        if obs.shape[0] != idx.shape[0]:
+            raise ValueError("one box per index")
+        _lib.check(self._lib.gmt_update_obstacles(self._handle, idx.ctypes.data, obs.ctypes.data, idx.shape[0]),
+                   "gmt_update_obstacles")
+
     def insert_states(self, states_xyt, disk_radius=4 * math.sqrt(2)):
         """Extension: append states (e.g. the vehicle's current pose as a new start) to the resident
         roadmap without rebuilding the neighbour lists; returns their ids.  The reference rebuilds the whole
@@ -128,8 +144,8 @@ class GMT(object):
         if self.start != iter_parameters['start'] and len(self.route) > 2:
             del self.route[-1]                                 # gmt_planner.py:68-69
 
-        self.obstacles = iter_parameters['obstacles']
-        self.num_obs = iter_parameters['num_obs']
+        self.obstacles = iter_parameters.get('obstacles')
+        self.num_obs = iter_parameters.get('num_obs')
         self.start = iter_parameters['start']
         self.goal = iter_parameters['goal']
         self.radius = iter_parameters['radius']
@@ -184,6 +200,14 @@ class GMT(object):
     # ---- gmt_planner.py:109-239 ------------------------------------------------------------------
     def run_step(self, iter_parameters, iter_limit=1000, debug=False, time=False):
         self.step_init(iter_parameters, debug)
+        if self.obstacles is None:                       # extension: plan against the resident obstacle set
+            want_trace = bool(debug or time)
+            _lib.check(self._lib.gmt_set_trace(self._handle, 1 if want_trace else 0), "gmt_set_trace")
+            res = _lib.GmtResult()
+            rc = self._lib.gmt_plan_resident(self._handle, int(self.start), int(self.goal), float(np.float32(self.radius)),
+                                             float(self.threshold[0]), int(iter_limit), C.byref(res))
+            _lib.check(rc, "gmt_plan_resident")
+            return self._finish(res, want_trace, debug, time)
         num_obs = int(np.asarray(self.num_obs).reshape(-1)[0])
         # extension (not in the reference): iter_parameters['obstacle_format'] = 'oriented' -> rows
         # [centre_x, centre_y, half_x, half_y, angle_rad]; default: the reference's [xa, ya, xb, yb]
@@ -207,6 +231,9 @@ class GMT(object):
                                     obs.ctypes.data if num_obs > 0 else None, num_obs, int(iter_limit),
                                     C.byref(res))
         _lib.check(rc, "gmt_plan")
+        return self._finish(res, want_trace, debug, time)
+
+    def _finish(self, res, want_trace, debug, time):
         self.last_result = res
         self.iterations = res.iterations
         self.status = res.status

@@ -654,3 +654,35 @@ def test_tiny_pair_list_forces_segmented_open_list(GMT, oracles, monkeypatch, wi
                              it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=200)
     g.run_step(it, iter_limit=200, debug=True)
     _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "pair_cap 256")
+
+
+def test_obstacle_deltas_on_the_resident_set(GMT):
+    """a resident obstacle set, plans without any upload (iter_parameters['obstacles'] = None) and
+    in-place replacement of a few boxes must plan exactly like run_step with the full arrays."""
+    import _lib
+    init, it, meta = _world(None, 2000, 20, 19)
+    full = GMT(init)
+    g = GMT(init)
+    obs = np.ascontiguousarray(it['obstacles'], np.float32).copy()
+    g.set_obstacles(obs, it['num_obs'])
+    q = dict(it, obstacles=None, num_obs=None)
+    assert list(g.run_step(q, iter_limit=200)) == list(full.run_step(it, iter_limit=200))
+    assert np.array_equal(g.parent, full.parent)
+    parent0 = g.parent.copy()
+    assert len(full.route) > 6
+    # move three boxes (two consecutive indices, one apart) next to the route
+    route = full.route
+    mid = init['states'][route[len(route) // 2]]
+    idx = np.array([4, 5, 17], np.int32)
+    new = np.array([[mid[0] - 1.5, mid[1] - 1.5, mid[0] + 1.5, mid[1] + 1.5],
+                    [mid[0] + 6.0, mid[1] + 2.0, mid[0] + 9.0, mid[1] + 4.0],
+                    [mid[0] - 9.0, mid[1] - 4.0, mid[0] - 6.0, mid[1] - 2.0]], np.float32)
+    g.update_obstacles(idx, new)
+    obs[idx] = new
+    r1 = list(g.run_step(q, iter_limit=200))
+    r2 = list(full.run_step(dict(it, obstacles=obs), iter_limit=200))
+    assert r1 == r2 and np.array_equal(g.parent, full.parent)
+    assert np.array_equal(g.dev_cost.view(np.uint32), full.dev_cost.view(np.uint32))
+    assert not np.array_equal(g.parent, parent0)                                       # (and the tree did change)
+    with pytest.raises(_lib.GmtError):
+        g.update_obstacles([20], new[:1])                                              # index out of range
