@@ -26,13 +26,9 @@ print('iter ms', np.round(el, 3).tolist())
 out = (C.c_ulonglong * 8)()
 g._lib.gmt_debug_counters(g._handle, out)
 v = list(out)
-print('leader time: phase A+barrier %.3f ms, select+barrier %.3f ms, eval+barrier %.3f ms, sweep+barrier %.3f ms; pairs %d'
+print('leader time: frontier+barrier %.3f ms, select+barrier %.3f ms, (unused) %.3f ms, connect+barrier %.3f ms; pairs %d'
       % (v[0] * 1e-6, v[1] * 1e-6, v[2] * 1e-6, v[4] * 1e-6, v[3]))
-nx = sum(e['xSize'] for e in g.trace if e['xSize'] > 0)
-print('generate per x (group cycles): scan+geom %.0f, seed eval+sweep %.0f, compaction %.0f, eval+append %.0f; x total %d, survivors/x %.1f'
-      % (v[4] / nx, v[5] / nx, v[6] / nx, v[7] / nx, nx, v[3] / nx))
 for bps, thr in ((1, 128), (1, 256), (1, 512), (2, 256), (4, 128), (8, 64)):
     us = C.c_float()
     g._lib.gmt_debug_barrier_us(g._handle, bps, thr, 2000, C.byref(us))
     print('grid barrier: %d blocks/SM x %d threads: %.2f us' % (bps, thr, us.value))
-print('sweep outcomes in the sweep phase: free %d, hit in first arc round %d, hit later %d' % (v[5], v[6], v[7]))
