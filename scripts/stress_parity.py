@@ -12,7 +12,7 @@ build_oracle.build_port()
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 oracle = OraclePort("cuda")
-t0, cases, nodes, worst = time.time(), 0, 0, 0.0
+t0, cases, nodes, worst, batches = time.time(), 0, 0, 0.0, 0
 while time.time() - t0 < budget:
     n = int(rng.integers(300, 3500)); m = int(rng.integers(0, 50)); seed = int(rng.integers(0, 1 << 30))
     mode = "lattice" if rng.random() < 0.2 else "uniform"
@@ -73,8 +73,25 @@ while time.time() - t0 < budget:
     if g.status == 0 or r["route"]:
         assert route == r["route"] or len(diff) > 0, tag
     cases += 1; nodes += int(fin.sum())
+    # the batched entry on the same world: 6 random queries in one launch == 6 single plans (corner boxes only)
+    if not oriented and rng.random() < 0.5:
+        import _lib
+        obs = np.ascontiguousarray(it['obstacles'], np.float32)
+        mm = int(it['num_obs'][0])
+        _lib.check(g._lib.gmt_set_obstacles(g._handle, obs.ctypes.data if mm else None, mm), "set")
+        qs = rng.integers(0, g.n, 6).astype(np.int32)
+        res0, _ = sw.plan_batch(g, qs, np.full(6, -1, np.int32), radius=radius, iter_limit=limit)
+        qg = np.array([r_.farthest_frontier if r_.farthest_frontier >= 0 else int(s_) for r_, s_ in zip(res0, qs)], np.int32)
+        res, routes = sw.plan_batch(g, qs, qg, radius=radius, iter_limit=limit, route_stride=256)
+        for k in range(6):
+            single = GMT(init, words=words)
+            rs = list(single.run_step(dict(it, start=int(qs[k]), goal=int(qg[k])), iter_limit=limit))
+            assert (res[k].status, res[k].iterations) == (single.status, single.iterations), (tag, "batch", k)
+            if res[k].status == 0:
+                assert [int(v) for v in routes[k, :res[k].route_len]] == rs, (tag, "batch route", k)
+        batches += 1
 oracle.set_extensions(4, False)
 print("stress parity: %d random plans (worlds of 300-3500 states, 0-50 obstacles, radii 1-3, 4 / 6 words, corner / oriented boxes, "
       "lean / wide kernels, warp groups, tiny pair lists, masks on / off) in %.0f s: every status, iteration count, wavefront set and "
-      "parent equal to the CPU oracle; %d connected nodes, largest relative cost difference %.2e"
-      % (cases, time.time() - t0, nodes, worst))
+      "parent equal to the CPU oracle; %d connected nodes, largest relative cost difference %.2e; %d batches of 6 queries "
+      "equal to single plans" % (cases, time.time() - t0, nodes, worst, batches))
