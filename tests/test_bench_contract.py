@@ -1,0 +1,44 @@
+"""CPU: bench.py's contract where it can be checked without a GPU -- the reference arm prints the agreed JSON
+line (it times the reference's own kernels compiled for the host, or the C port), and the own arm refuses to
+run without a CUDA device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + list(args), cwd=ROOT, env=e,
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+
+
+def test_reference_arm_prints_the_contract_line():
+    res = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-budget", "1")
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "gmt_plans_per_sec" and d["unit"] == "plans/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["config"]["workload"].startswith("cfg2")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    res = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", env={"RANK": "1", "WORLD_SIZE": "2"})
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_own_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    res = _run("--steps", "1", "--warmup", "3")
+    assert res.returncode != 0 and "no CUDA device" in (res.stderr + res.stdout)
