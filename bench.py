@@ -375,6 +375,16 @@ def run_b200(args):
     }
     if edge:
         line["edge_kernel"]["fp32_frac"] = edge["edge_checks_per_s"] * f_edge(m) * 1e-12 / fp32_peak.value
+    # the HBM view of the same kernel, for completeness: measured DRAM bytes per launch (ncu) over its duration
+    # against the measured copy bandwidth of MEASURED_PEAKS.json -- it shows how far from memory-bound the path is
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = None
+    traffic = line["roofline"]["traffic"]
+    line["roofline"]["hbm"] = {"achieved": (traffic / kern_s * 1e-9) if traffic else None, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": (traffic / kern_s * 1e-9 / hbm_peak) if traffic and hbm_peak else None,
+                               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "absent"}
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):          # workload facts to cache under profiles/ (committed by hand)
         with open(os.path.join(out_dir, "workload_cfg%d.json" % args.config), "w") as f:
