@@ -73,9 +73,18 @@ class OraclePort:
                                       _u32p, _f32p]
         L.gmto_get_path.restype = C.c_int
         L.gmto_get_path.argtypes = [_i32p, C.c_int, C.c_int, _i32p, C.c_int]
+        L.gmto_set_num_threads.restype = C.c_int
+        L.gmto_set_num_threads.argtypes = [C.c_int]
         L.gmto_set_extensions.restype = None
         L.gmto_set_extensions.argtypes = [C.c_int, C.c_int]
         self.words, self.oriented = 4, False
+
+    def set_num_threads(self, n):
+        """OpenMP threads of the x loops (returns the team size in effect)."""
+        return int(self.lib.gmto_set_num_threads(int(n)))
+
+    def num_threads(self):
+        return int(self.lib.gmto_set_num_threads(0))
 
     def set_extensions(self, words=4, oriented=False):
         """Extension mode (parity unpinned, see gmt_oracle.c): 6 words and / or oriented rectangles
@@ -235,6 +244,10 @@ class RefHost:
 
     def num_threads(self):
         return int(self.lib.ref_num_threads())
+
+    def set_num_threads(self, n):
+        self.lib.ref_set_num_threads(int(n))
+        return self.num_threads()
 
     def word(self, word, start, end, r_min, obstacles=None, num_obs=0):
         obs, m = _obstacles(obstacles if obstacles is not None else [], [num_obs])

@@ -54,6 +54,14 @@ __attribute__((visibility("default"))) int ref_num_threads(void)
 #endif
 }
 
+// bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: the arm asks for all cores itself
+__attribute__((visibility("default"))) void ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 // dubinConnection over ceil(xSize/tpb) blocks of tpb threads (gmt_planner.py:200-201).
 __attribute__((visibility("default"))) void ref_dubin_connection(
     float *cost, int *parent, int *x, int *y, float *states, int *open, int *unexplored, int xSize,

@@ -92,6 +92,10 @@ class GMT(object):
         _lib.check(self._lib.gmt_set_words(self._handle, int(words)), "gmt_set_words")
         self.words = int(words)
 
+    def set_option(self, name, value):
+        """Tuning / test knob of the library (gmt_set_option): never changes a result."""
+        _lib.check(self._lib.gmt_set_option(self._handle, str(name).encode(), int(value)), "gmt_set_option")
+
     def set_obstacles(self, obstacles, num_obs=None):
         """Extension: make an obstacle set resident on the device; later run_step calls whose
         iter_parameters['obstacles'] is None plan against it without any upload."""

@@ -32,6 +32,15 @@ def test_library_exports_every_declared_symbol(gmt_lib):
     assert gmt_lib.gmt_version() >= 100
 
 
+def test_library_exports_nothing_the_header_does_not_declare():
+    """exports of libgmt_b200.so with the gmt_ prefix == the header's declarations (no undeclared debug hooks)."""
+    import subprocess
+    lib = os.path.join(ROOT, "robot-parallel-motion-planning_b200", "libgmt_b200.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], stdout=subprocess.PIPE, text=True, check=True).stdout
+    exported = sorted({l.split()[-1] for l in out.splitlines() if l.split() and l.split()[-1].startswith("gmt_")})
+    assert exported == _declared()
+
+
 def test_no_cpu_fallback_without_a_device(gmt_lib):
     import torch
     if torch.cuda.is_available():

@@ -423,12 +423,12 @@ def test_blocked_arrival_masks_do_not_change_results(GMT, oracles, monkeypatch):
     init, it, meta = _world(None, 3000, 30, 61)
     r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
                              it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=200)
-    monkeypatch.setenv("GMT_MASK_MIN_Y", "0")
     g = GMT(init)
+    g.set_option("mask_min_y", 0)
     g.run_step(it, iter_limit=200, debug=True)
     _compare_plan(g, r["status"], r["iterations"], r["parent"], r["cost"], r["trace"], init['states'], "masks on")
     parent_on, cost_on, swept_on = g.parent.copy(), g.dev_cost.copy(), g.last_result.word_checks
-    monkeypatch.setenv("GMT_MASK_MIN_Y", "1000000")
+    g.set_option("mask_min_y", 1000000)
     g.run_step(it, iter_limit=200)
     assert np.array_equal(g.parent, parent_on)
     assert np.array_equal(g.dev_cost.view(np.uint32), cost_on.view(np.uint32))
@@ -621,9 +621,9 @@ def test_several_warps_per_candidate_do_not_change_results(GMT, oracles, monkeyp
     ref = GMT(init)
     route = list(ref.run_step(it, iter_limit=200))
     parent, cost = ref.parent.copy(), ref.dev_cost.copy()
-    monkeypatch.setenv("GMT_SELECT_K", str(k))
-    monkeypatch.setenv("GMT_WIDE", "1")          # the plan-kernel instantiation with warp groups (default from 30k nodes)
+    monkeypatch.setenv("GMT_SELECT_K", str(k))   # (read once, at gmt_create)
     g = GMT(init)
+    g.set_option("wide", 1)                      # the plan-kernel instantiation with warp groups (default from 30k nodes)
     assert list(g.run_step(it, iter_limit=200, debug=True)) == route
     assert np.array_equal(g.parent, parent) and np.array_equal(g.dev_cost.view(np.uint32), cost.view(np.uint32))
     r = oracles["cuda"].plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], it['goal'],
