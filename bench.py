@@ -1,25 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- GMT* plans/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+"""bench.py -- GMT* plans/sec on B200 (BASELINE.json metric), ONE JSON line on stdout.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--only NAME] [--words 6] [--oriented]
 
-A "step" is ONE plan of the hot path (GMT.run_step: wavefront expansion + Dubins edge costs +
-swept-path collision) on the BASELINE.json configuration `--config` (default 2: single query,
-10k samples, 100 obstacles, the first single-GPU configuration the metric is quoted on).
+Headline workload (the same at every N, so the driver's 1/2/4/8 run is a strong-scaling curve): BASELINE
+config 4 -- a batch of 4096 independent start/goal queries on the 10k-sample / 100-obstacle map, the query list
+split contiguously over the ranks, no collective on the data path.  It is the largest configuration of the metric
+that fits one GPU.  A "step" is one pass of the hot path over this rank's share of the batch (ONE launch of the
+persistent plan kernel in team mode).
 
-* value        plans/s with the roadmap AND the obstacle set resident in HBM (gmt_plan_resident),
-               CUDA events on the launching stream, L2 flushed between timed plans.
-* e2e          the same metric through the reference-facing call GMT.run_step(iter_parameters)
-               with HOST numpy buffers: obstacle upload (pinned staging -> H2D) and result/route
-               download (D2H) inside the timed region.
-* roofline     dominant kernel gmt_plan_kernel: algorithmic FP32 work (reference edge checks
-               sum|X|*|Y| x F_edge(m)) / its CUDA-event duration, against the FP32 FMA
-               peak measured live on this GPU (gmt_measure_fp32_peak).
-* cpu_baseline the reference's own kernels compiled for the host (oracle/_ref, kind "reference") or
-               the C restatement (kind "port") on this box's cores, on a bounded sample of the plan.
-N > 1 (torchrun): independent queries, one per rank and step, no collective on the data path
-("weak" scaling); NCCL is used only for the barrier and the max-over-ranks of the timings.
---impl reference times the reference CPU implementation instead (rank 0 only).
+* value     plans/s with roadmap, obstacle set AND query list resident in HBM (gmt_set_queries once,
+            gmt_plan_queries per step), CUDA events on the launching stream (an explicit torch stream the handle
+            is told to use), L2 flushed before every timed step, max over ranks.
+* e2e       the same through the host-buffer call gmt_plan_batch (numpy start/goal arrays in, result structs and
+            routes out), wall clock around the call, copies inside.
+* sub       records of the other BASELINE configurations, measured in the same run:
+            N = 1: cfg2 / cfg3 single-query latency (resident and through GMT.run_step with host buffers), "cfg3u"
+            (100k uniform samples, 500 obstacles, a goal ~150 wavefronts away: the driver-timed form of the
+            "100k-sample plan < 10 ms" target), the edge kernel (Dubins edge checks/s), the reference's own kernels
+            on this GPU (gpu_reference, with a bit-exact comparison of the two trees) and on the host cores;
+            every N: cfg5, ONE plan on the 1M-sample roadmap -- single GPU at N = 1, node-range sharding with the
+            in-kernel NVLink exchange at N > 1 (the NCCL all-reduce(min) form is timed beside it).
+* roofline  dominant kernel gmt_plan_kernel: algorithmic FP32 work (reference edge checks x F_edge(m))
+            over its CUDA-event time against the FP32 FMA peak measured live; `executed_frac` = the same with the
+            work the kernel actually did (pairs evaluated, words swept); `ncu` = issue-slot / pipe utilisation of
+            the committed ncu capture of this kernel (profiles/).
+* cpu_baseline  the reference's kernels compiled for the host (oracle/_ref, kind "reference"; else the C port) on
+            this box's cores, on a bounded sample of the batch.
+--impl reference times that CPU implementation alone (rank 0 only), same config dict, metric and unit.
+--only cfg1|cfg2|cfg3|cfg3u|cfg4|cfg5 restricts the run to one workload (development).
 """
 import argparse
 import json
@@ -39,12 +48,19 @@ for _p in (ROOT, PKG):
 
 METRIC = "gmt_plans_per_sec"
 UNIT = "plans/s"
-WORKLOADS = {4: "cfg4: batch of 4096 independent start/goal queries on a 10k-sample map, sharded by rank, no collective",
-             1: "cfg1: single query, 2k samples, 20 obstacles",
-             2: "cfg2: single query, 10k samples, 100 obstacles",
-             3: "cfg3: single query, 100k samples, road lattice, 2k obstacles",
-             5: "cfg5: single query on ONE 1M-sample roadmap (2k obstacles), edge evaluation sharded by node range "
-                "over the GPUs, per-wavefront exchange of the packed cost/parent keys"}
+Q_BATCH = 4096
+ROUTE_STRIDE = 128
+WORKLOADS = {
+    "cfg1": "cfg1: single query, 2k samples, 20 obstacles",
+    "cfg2": "cfg2: single query, 10k samples, 100 obstacles",
+    "cfg3": "cfg3: single query, 100k samples, road lattice, 2k obstacles",
+    "cfg3u": "cfg3u: single query, 100k uniform samples, 500 obstacles, goal ~150 wavefronts away",
+    "cfg4": "cfg4: batch of 4096 independent start/goal queries on a 10k-sample / 100-obstacle map, split over the "
+            "GPUs by rank, no collective",
+    "cfg5": "cfg5: single query on ONE 1M-sample roadmap (2k obstacles), edge evaluation sharded by node range over "
+            "the GPUs, per-wavefront exchange of the packed cost/parent keys over NVLink",
+}
+SINGLE_CONFIG = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg5": 5}
 
 
 def f_edge(m):
@@ -52,8 +68,23 @@ def f_edge(m):
     return 4.0 * (1142.0 + 604.0 * m)
 
 
+def f_executed(evals, checks, nw=4):
+    """Op-equivalents of the work a plan actually did, in SURVEY 8d's units: every evaluated pair pays the
+    tangent construction + cost of its words (1142 - 401 - 401 - 254 = 86 per word without the sample points);
+    every swept word pays its 150 sample points (401 + 401 + 254) and, against the obstacle grid, about one cell
+    lookup (~12) per point instead of 4 compares x m boxes."""
+    return float(evals) * nw * 86.0 + float(checks) * (1056.0 + 150.0 * 12.0)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def headline_config():
+    """The `config` object of the JSON line: static, identical in both arms."""
+    return {"workload": WORKLOADS["cfg4"], "n": 10000, "m": 100, "seed": 22, "queries": Q_BATCH, "iter_limit": 1000,
+            "radius": 2.0, "threshold": 1.0, "goals": "farthest state that enters a wavefront from each start",
+            "sub_workloads": [WORKLOADS[k] for k in ("cfg2", "cfg3", "cfg3u", "cfg5")]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -129,98 +160,183 @@ def gpu_uuid(torch, dev, local):
     return "GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local)
 
 
+def profile_json(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return {}
+    return {}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's CPU implementation on a bounded sample
+# worlds
 # --------------------------------------------------------------------------------------------------
-def explore_oracle(init, it):
-    """CPU twin of synthetic_world.explore_cuda: ids that ever enter a wavefront (oracle, no goal)."""
-    from oracle import build_oracle
-    from oracle.gmt_oracle import OraclePort
-    build_oracle.build_port()
-    r = OraclePort("libm").plan(init['states'], init['neighbors'], init['num_neighbors'], it['start'], -1,
-                                it['radius'], it['threshold'], it['obstacles'], it['num_obs'], iter_limit=1000)
-    members = [e["G"] for e in r["trace"] if e["gSize"] > 0 and "G" in e]
-    return np.unique(np.concatenate(members)) if members else np.zeros(0, np.int32)
-
-
-def bench_query(config, init, it, meta, explore):
-    """The benchmark query of a configuration: start = state nearest (0.1S, 0.1S), goal = the state
-    nearest (0.9S, 0.9S) that the reference's GMT variant can reach from it (see
-    synthetic_world.pick_reachable_goal).  Cached in profiles/workload_cfgN.json once measured."""
+def make_named_world(name, cpu=False, device=0):
+    """(init, it, meta) of a named workload; cpu=True builds it with the NumPy restatements (bit-identical to the
+    CUDA builders, tests/test_world_oracle.py + tests/test_gpu_parity.py) so that the CPU arm needs no GPU."""
     import synthetic_world as sw
-    cached = workload_meta(config)
-    if cached.get("n") == meta["n"] and cached.get("m") == meta["m"] and cached.get("seed") == meta["seed"] \
-            and cached.get("start") == int(it['start']):
-        return dict(it, goal=int(cached["goal"]))
-    goal = sw.pick_reachable_goal(init, it, meta["side"], explore=explore)
-    log("bench query for cfg%d: start %d goal %d (not cached in profiles/)" % (config, it['start'], goal))
-    return dict(it, goal=goal)
+    kw = {}
+    if cpu:
+        from oracle.world_oracle import build_neighbors, sample_states
+        kw = dict(sampler=sample_states, neighbor_builder=build_neighbors)
+    else:
+        kw = dict(sampler=lambda *a: sw.cuda_sampler(*a, device=device),
+                  neighbor_builder=lambda s_, r_: sw.cuda_neighbor_builder(s_, r_, device=device))
+    if name == "cfg3u":
+        return sw.make_world(n=100000, m=500, seed=31, mode="uniform", layout="uniform", **kw)
+    if name == "cfg4":
+        return sw.make_world(4, **kw)
+    return sw.make_world(SINGLE_CONFIG[name], **kw)
 
 
-def cpu_world(config):
-    """The same world as the GPU arm, built by the NumPy restatements (bit-identical, tested)."""
+def cached_goal(name, it, meta):
+    c = profile_json("workload_%s.json" % name)
+    if c.get("n") == meta["n"] and c.get("m") == meta["m"] and c.get("seed") == meta["seed"] and \
+            c.get("start") == int(it['start']) and "goal" in c:
+        return int(c["goal"]), c
+    return None, c
+
+
+def bench_query(name, init, it, meta, device=0):
+    """Benchmark query of a single-plan workload: start = state nearest (0.1 S, 0.1 S); goal = the state nearest
+    (0.9 S, 0.9 S) among those the reference's GMT variant reaches from it (synthetic_world.pick_reachable_goal),
+    for cfg3u the reachable state farthest from the start.  Cached in profiles/workload_<name>.json."""
     import synthetic_world as sw
-    from oracle.world_oracle import build_neighbors, sample_states
-    init, it, meta = sw.make_world(config, sampler=sample_states, neighbor_builder=build_neighbors)
-    return init, bench_query(config, init, it, meta, explore_oracle), meta
+    goal, c = cached_goal(name, it, meta)
+    if goal is not None:
+        return dict(it, goal=goal), c
+    reach = sw.explore_cuda(init, it, device=device)
+    st = init['states']
+    if len(reach) == 0:
+        return it, {}
+    if name == "cfg3u":
+        d = (st[reach, 0].astype(np.float64) - st[it['start'], 0]) ** 2 + (st[reach, 1].astype(np.float64) - st[it['start'], 1]) ** 2
+        goal = int(reach[int(np.argmax(d))])
+    else:
+        goal = sw.pick_reachable_goal(init, it, meta["side"], explore=lambda a, b: reach)
+    log("bench query for %s: start %d goal %d (not cached in profiles/), %d reachable states" % (name, it['start'], goal, len(reach)))
+    return dict(it, goal=goal), {"reach_fraction": len(reach) / float(meta["n"])}
 
 
+def save_workload(name, rec):
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):          # workload facts to cache under profiles/ (committed by hand)
+        with open(os.path.join(out_dir, "workload_%s.json" % name), "w") as f:
+            json.dump(rec, f)
+
+
+def batch_queries(g, meta, device=0):
+    """The 4096 (start, goal) pairs of cfg4 (same list on every rank and in both arms): cached in
+    profiles/workload_cfg4.json (the goals need one goal-less GPU batch), else computed."""
+    import synthetic_world as sw
+    c = profile_json("workload_cfg4.json")
+    if c.get("n") == meta["n"] and c.get("seed") == meta["seed"] and len(c.get("starts", [])) == Q_BATCH:
+        return np.array(c["starts"], np.int32), np.array(c["goals"], np.int32), c
+    if g is None:
+        return None, None, {}
+    starts, goals = sw.make_reachable_queries(g, meta["n"], Q_BATCH, meta["seed"] + 7)
+    return starts, goals, {}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's CPU implementation on a bounded sample (reference arm and cpu_baseline leg)
+# --------------------------------------------------------------------------------------------------
 def cpu_backend():
     from oracle import build_oracle
     from oracle.gmt_oracle import OraclePort, RefHost
     if RefHost.available():
-        ref = RefHost()
-        return ref, "reference", ref.num_threads()
+        return RefHost(), "reference"
     build_oracle.build_port()
-    return OraclePort("libm"), "port", os.cpu_count() or 1
+    return OraclePort("libm"), "port"
 
 
-def cpu_sample(init, it, backend, budget_s, total_pairs):
-    """Runs the restated GMT.run_step over the reference kernels for ~budget_s seconds of
-    dubinConnection work.  Returns (plans_per_s, description)."""
+def cpu_batch_sample(init, it, backend, starts, goals, pairs_total, first, count, budget_s, threads):
+    """Plans queries first .. first+count-1 of the batch with the restated GMT.run_step over the reference kernels,
+    `threads` plans at a time, one host thread per plan (independent queries are the natural unit of CPU
+    parallelism for a batch; the library call releases the GIL).  A plan that exceeds budget_s seconds of
+    dubinConnection work is cut there and counted as the fraction of its edge checks it got through.
+    Returns (plans per second, description)."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle.gmt_oracle import OracleGMT
-    g = OracleGMT(init, backend)
+
+    def one(i):
+        if hasattr(backend, "set_num_threads"):
+            backend.set_num_threads(1)          # (OpenMP's thread-count setting is per calling thread)
+        g = OracleGMT(init, backend)
+        g.run_step(dict(it, start=int(starts[i]), goal=int(goals[i])), iter_limit=1000, budget_s=budget_s)
+        if g.status in (0, 1):
+            return 1.0, g.edge_pairs, True
+        tot = pairs_total[i] if pairs_total is not None else 0
+        return (min(1.0, g.edge_pairs / float(tot)) if tot else 0.0), g.edge_pairs, False
+
+    idx = [(first + k) % len(starts) for k in range(count)]
     t0 = time.perf_counter()
-    g.run_step(it, iter_limit=1000, budget_s=budget_s)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(one, idx))
     wall = time.perf_counter() - t0
-    if g.status in (0, 1):
-        return 1.0 / wall, "whole plan (%d wavefronts, %d edge checks) in %.1f s" % (g.iterations, g.edge_pairs, wall)
-    rate = g.edge_pairs / max(wall, 1e-9)
-    if not total_pairs:
-        return float("nan"), "first %d wavefronts only; total edge checks unknown" % g.iterations
-    return rate / total_pairs, ("first %d wavefronts = %d of %d edge checks (brute-force dubinConnection) in %.1f s; "
-                                "plan time extrapolated by edge-check count" % (g.iterations, g.edge_pairs,
-                                                                                total_pairs, wall))
+    done = sum(r[0] for r in res)
+    whole = sum(1 for r in res if r[2])
+    pairs = sum(r[1] for r in res)
+    desc = ("%d queries of the batch on %d host threads (one plan per thread, brute-force dubinConnection): %d whole "
+            "plans, %d cut after %.0f s and counted by edge-check fraction; %d edge checks in %.1f s"
+            % (count, threads, whole, count - whole, budget_s, pairs, wall))
+    return done / wall, desc
 
 
-def workload_meta(config):
-    path = os.path.join(ROOT, "profiles", "workload_cfg%d.json" % config)
-    if os.path.exists(path):
-        return json.load(open(path))
-    return {}
+def cpu_edge_checks(init, it, backend, pairs, threads):
+    """Dubins edge checks/s of the reference's computeDubinsCost on the host: `pairs` neighbour pairs, all 4 words,
+    against the obstacle set (kernel.py:418-431 per pair)."""
+    rng = np.random.default_rng(7)
+    nbr, num = init['neighbors'], init['num_neighbors']
+    rows = np.repeat(np.arange(len(num), dtype=np.int32), num)
+    sel = rng.integers(0, len(nbr), pairs)
+    y, x = np.ascontiguousarray(rows[sel]), np.ascontiguousarray(nbr[sel].astype(np.int32))
+    if hasattr(backend, "set_num_threads"):
+        backend.set_num_threads(threads)
+    t0 = time.perf_counter()
+    backend.edge_costs(init['states'], y, x, it['radius'], it['obstacles'], it['num_obs'])
+    return pairs / (time.perf_counter() - t0)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    init, it, meta = cpu_world(args.config)
-    backend, kind, cores = cpu_backend()
-    total = workload_meta(args.config).get("edge_pairs", 0)
-    vals, desc = [], ""
-    # every step is a bounded sample; the whole run stays within a few minutes whatever K is
-    budget = min(args.cpu_budget, 150.0 / max(args.warmup + args.steps, 1))
-    for s in range(args.warmup + args.steps):
-        v, desc = cpu_sample(init, it, backend, budget, total)
+    cores = host_cores()
+    init, it, meta = make_named_world("cfg4", cpu=True)
+    backend, kind = cpu_backend()
+    starts, goals, cache = batch_queries(None, meta)
+    note = ""
+    if starts is None:       # no cached list (it needs one GPU pass): uniform pairs at least S/2 apart instead
+        import synthetic_world as sw
+        starts, goals = sw.make_queries(init['states'], meta["side"], Q_BATCH, meta["seed"] + 7)
+        note = " (profiles/workload_cfg4.json missing: uniform start/goal pairs)"
+    pairs_total = cache.get("edge_pairs")
+    steps = args.warmup + args.steps
+    budget = min(args.cpu_budget, 150.0 / max(steps, 1))
+    vals, walls, desc = [], [], ""
+    for s in range(steps):
+        t0 = time.perf_counter()
+        v, desc = cpu_batch_sample(init, it, backend, starts, goals, pairs_total, s * cores, cores, budget, cores)
         if s >= args.warmup:
             vals.append(v)
+            walls.append(time.perf_counter() - t0)
         log("reference step %d: %.6g plans/s (%s)" % (s, v, desc))
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value if value > 0 else None,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.config], "n": meta["n"], "m": meta["m"], "seed": meta["seed"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": headline_config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc + note},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -230,100 +346,365 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # own arm
 # --------------------------------------------------------------------------------------------------
-def run_b200(args):
+class Ctx:
+    """Per-process GPU context of the own arm: device, explicit stream, library, flush buffer, barrier."""
+
+    def __init__(self):
+        import torch
+        import _lib
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the planner has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.lib = _lib.load()
+        self._lib = _lib
+        # an EXPLICIT stream: the library treats a NULL stream as "use the handle's own", so torch's default stream
+        # (handle 0) would leave the timing events and the L2 flush on another, unordered stream
+        self.stream = torch.cuda.Stream(self.dev)
+        assert self.stream.cuda_stream != 0
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)        # > 126 MB L2
+
+    def bind(self, g):
+        import ctypes as C
+        self._lib.check(self.lib.gmt_set_stream(g._handle, C.c_void_p(self.stream.cuda_stream)), "gmt_set_stream")
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def events(self, k):
+        return [(self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+
+    def timed(self, K, fn, pre=None):
+        """K timed calls of fn() on the explicit stream, L2 flushed before each: (device seconds by CUDA events,
+        host wall seconds with a synchronize on both sides of every call)."""
+        torch = self.torch
+        ev = self.events(K)
+        wall = 0.0
+        with torch.cuda.stream(self.stream):
+            for k in range(K):
+                self.flush.fill_(k & 0xFF)                                       # evict L2 (same stream: ordered)
+                if pre:
+                    pre(k)
+                self.stream.synchronize()
+                ev[k][0].record(self.stream)
+                t0 = time.perf_counter()
+                fn()
+                self.stream.synchronize()
+                wall += time.perf_counter() - t0
+                ev[k][1].record(self.stream)
+            self.stream.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) * 1e-3, wall
+
+
+def time_single(ctx, name, K=30, words=4, oriented=False):
+    """Single-query workload: resident latency (gmt_plan_resident, CUDA events) and e2e latency (GMT.run_step with
+    host obstacle buffers).  Returns the sub-record."""
     import ctypes as C
-
-    import torch
-    import _lib
-    import synthetic_world as sw
     from gmt_planner import GMT
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the planner has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = _lib.load()
-    dev = torch.device("cuda", local)
-
-    init, it, meta = sw.make_world(args.config)           # CUDA sampler + CUDA neighbour search
-    it = bench_query(args.config, init, it, meta, None)
+    _lib, lib = ctx._lib, ctx.lib
+    init, it, meta = make_named_world(name, device=ctx.local)
+    it, cache = bench_query(name, init, it, meta, device=ctx.local)
     n, m = meta["n"], meta["m"]
-    g = GMT(init, device=local)
-    stream = torch.cuda.current_stream(dev)
-    _lib.check(lib.gmt_set_stream(g._handle, C.c_void_p(stream.cuda_stream)), "gmt_set_stream")
-    # weak scaling: every rank plans the configuration's query on its own replica of the roadmap --
-    # independent plans, identical work per GPU, nothing exchanged on the data path
+    g = GMT(init, device=ctx.local, words=words)
+    ctx.bind(g)
     start, goal = int(it['start']), int(it['goal'])
-    obs = np.ascontiguousarray(it['obstacles'], np.float32)
     radius, thr0 = float(np.float32(it['radius'])), float(np.float32(it['threshold']))
-    _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+    obs = np.ascontiguousarray(it['obstacles'], np.float32)
+    if oriented:
+        # the same boxes as oriented rectangles turned by seeded angles (extension mode, parity unpinned)
+        rng = np.random.default_rng(5)
+        lo, hi = np.minimum(obs[:, :2], obs[:, 2:]), np.maximum(obs[:, :2], obs[:, 2:])
+        rect = np.concatenate([(lo + hi) / 2, (hi - lo) / 2, rng.uniform(-np.pi, np.pi, (len(obs), 1))], 1).astype(np.float32)
+        it = dict(it, obstacles=rect, obstacle_format='oriented')
+        g.run_step(it, iter_limit=1000)
+    else:
+        _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
     res = _lib.GmtResult()
 
     def plan_resident():
         _lib.check(lib.gmt_plan_resident(g._handle, start, goal, radius, thr0, 1000, C.byref(res)), "gmt_plan_resident")
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    for _ in range(3):
+        plan_resident()
+        g.run_step(it, iter_limit=1000)
+    kern = [0.0]
+
+    def timed_resident():
+        plan_resident()
+        kern[0] += res.device_ms
+    t_dev, _ = ctx.timed(K, timed_resident)
+    stats = dict(status=res.status, wavefronts=res.iterations, goal_cost=res.goal_cost, route_len=res.route_len,
+                 edge_checks=res.edge_pairs, pairs_evaluated=res.edge_evals, words_swept=res.word_checks)
+    dbg = (C.c_ulonglong * 8)()
+    lib.gmt_debug_counters(g._handle, dbg)
+    _, wall = ctx.timed(K, lambda: g.run_step(it, iter_limit=1000))
+    assert kern[0] * 1e-3 <= t_dev * 1.0005 + 1e-6, "plan kernels (%.4f ms) cannot outlast the events around them (%.4f ms)" % (kern[0], t_dev * 1e3)
+    st = init['states']
+    gd = float(np.hypot(st[goal, 0] - st[start, 0], st[goal, 1] - st[start, 1])) if goal >= 0 else None
+    rec = {"workload": WORKLOADS.get(name, name), "n": n, "m": m, "seed": meta["seed"], "words": words,
+           "obstacles": "oriented rectangles" if oriented else "corner boxes",
+           "resident_ms": t_dev / K * 1e3, "e2e_ms": wall / K * 1e3, "kernel_ms": kern[0] / K,
+           "plans_per_s_resident": K / t_dev, "plans_per_s_e2e": K / wall, "steps": K, "plan": stats,
+           "goal_distance_over_side": gd / meta["side"] if gd is not None else None,
+           "reach_fraction": cache.get("reach_fraction"),
+           "phase_us_per_wavefront": {"frontier": dbg[0] / 1e3 / max(res.iterations, 1), "select": dbg[1] / 1e3 / max(res.iterations, 1),
+                                      "connect": dbg[4] / 1e3 / max(res.iterations, 1)},
+           "h2d_bytes_per_step": int(16 * m), "d2h_bytes_per_step": int(512 + 4 * min(n + 1, 1024))}
+    rec["algorithmic_tflops"] = res.edge_pairs * f_edge(m) / (kern[0] / K * 1e-3) * 1e-12
+    rec["executed_tflops"] = f_executed(res.edge_evals, res.word_checks, words) / (kern[0] / K * 1e-3) * 1e-12
+    if not oriented and words == 4:
+        save_workload(name, {"n": n, "m": m, "seed": meta["seed"], "start": start, "goal": goal,
+                             "edge_pairs": res.edge_pairs, "wavefronts": res.iterations, "status": res.status,
+                             "goal_cost": res.goal_cost, "reach_fraction": cache.get("reach_fraction")})
+    return rec, (g, init, it, meta)
+
+
+def gpu_reference_leg(ctx, g, init, it, tag, budget_s=20.0):
+    """The reference's own kernels (ref_kernel.cubin) on THIS GPU under the restated GMT.run_step loop with
+    device-resident arrays -- a reported baseline and, because the same query was just planned by the CUDA path,
+    a bit-exact comparison of the two trees (status, iterations, parents, cost bit patterns)."""
+    from oracle.ref_gpu import RefGpu, RefGpuPlanner
+    if not RefGpu.available():
+        return {"unavailable": "oracle/_ref/ref_kernel.cubin did not travel to this box"}
+    ref = RefGpuPlanner(init)
+    ref.run_step(it, iter_limit=2, budget_s=budget_s)                     # warm-up (module load, allocator)
+    r = ref.run_step(it, iter_limit=1000, budget_s=budget_s)
+    out = {"workload": tag, "kind": "reference kernels (carla/kernel.py compiled for sm_100a) + restated host loop, "
+                                    "device-resident arrays, torch.cumsum for the three scans",
+           "status": r["status"], "wavefronts": r["iterations"], "seconds": r["seconds"], "edge_checks": r["edge_pairs"]}
+    if r["status"] in (0, 1):
+        out["plans_per_s"] = 1.0 / r["seconds"]
+        out["edge_checks_per_s"] = r["edge_pairs"] / r["seconds"]
+        g.run_step(it, iter_limit=1000)
+        parent, cost = g.parent, g.dev_cost
+        out["parity"] = {"status_equal": bool(g.status == r["status"]), "iterations_equal": bool(g.iterations == r["iterations"]),
+                         "parents_differing": int((parent != r["parent"]).sum()),
+                         "cost_bit_patterns_differing": int((cost.view(np.uint32) != r["cost"].view(np.uint32)).sum()),
+                         "nodes_connected": int((r["parent"] >= 0).sum()), "route_equal": bool(list(g.route) == r["route"])}
+    else:
+        out["note"] = "cut after %.0f s" % budget_s
+    return out
+
+
+def time_sharded(ctx, K=8):
+    """cfg5: ONE plan on the 1M-sample roadmap.  N = 1: the plain persistent plan.  N > 1: node-range sharding,
+    fused form (one launch per GPU, per-wavefront exchange over NVLink peer memory inside the kernel) timed with
+    CUDA events, max over ranks; the NCCL all-reduce(min) form once beside it; every rank's route must be the
+    single-GPU route."""
+    import ctypes as C
+    import multi_gpu
+    from gmt_planner import GMT
+    torch, _lib, lib = ctx.torch, ctx._lib, ctx.lib
+    rank, world = ctx.rank, ctx.world
+    init, it, meta = make_named_world("cfg5", device=ctx.local)
+    n, m = meta["n"], meta["m"]
+    goal, cache = cached_goal("cfg5", it, meta)
+    if goal is None:
+        if rank == 0:
+            it2, cache = bench_query("cfg5", init, it, meta, device=ctx.local)
+            goal = int(it2['goal'])
+        gt = torch.tensor([goal or 0], device=ctx.dev)
+        if ctx.dist is not None:
+            ctx.dist.broadcast(gt, 0)
+        goal = int(gt.item())
+    it = dict(it, goal=goal)
+    g = GMT(init, device=ctx.local)
+    ctx.bind(g)
+    with torch.cuda.stream(ctx.stream):
+        single = list(g.run_step(it, iter_limit=1000))                   # also the check value for the sharded forms
+    res1 = g.last_result
+    single_ms = res1.device_ms
+    if world > 1:
+        multi_gpu.open_peers(g, rank, world)
+
+        def step():
+            return multi_gpu.run_step_sharded_p2p(g, it, iter_limit=1000, rank=rank, world=world)
+    else:
+        def step():
+            return g.run_step(it, iter_limit=1000), g.last_result
+    out = {}
+    for _ in range(3):
+        out["route"], out["res"] = step()
+    ctx.barrier()
+
+    def timed_step():
+        out["route"], out["res"] = step()
+    t_dev, wall = ctx.timed(K, timed_step, pre=(lambda k: ctx.barrier()) if world > 1 else None)
+    ctx.barrier()
+    same = int(list(out["route"]) == single)
+    dbg = (C.c_ulonglong * 8)()
+    lib.gmt_debug_counters(g._handle, dbg)
+    phases = [dbg[0] / 1e3, dbg[1] / 1e3, dbg[4] / 1e3, dbg[2] / 1e3]
+    nccl_ms = 0.0
+    if world > 1:
+        multi_gpu.close_peers(g)
+        ctx.barrier()
+        with torch.cuda.stream(ctx.stream):
+            t0 = time.perf_counter()
+            r2, _res2, _steps2 = multi_gpu.run_step_sharded(g, it, iter_limit=1000, rank=rank, world=world)
+            torch.cuda.synchronize(ctx.dev)
+            nccl_ms = (time.perf_counter() - t0) * 1e3
+        same = int(same and list(r2) == single)
+    t_dev, wall, nccl_ms, single_ms = multi_gpu.max_over_ranks([t_dev, wall, nccl_ms, single_ms], device=ctx.dev)
+    flags = torch.tensor([same], device=ctx.dev)
+    ph = torch.tensor(phases, dtype=torch.float64, device=ctx.dev)
+    ph_max, ph_min = ph.clone(), ph.clone()
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(flags, op=ctx.dist.ReduceOp.MIN)
+        ctx.dist.all_reduce(ph_max, op=ctx.dist.ReduceOp.MAX)
+        ctx.dist.all_reduce(ph_min, op=ctx.dist.ReduceOp.MIN)
+    wf = max(res1.iterations, 1)
+    rec = {"workload": WORKLOADS["cfg5"], "n": n, "m": m, "seed": meta["seed"], "n_gpus": world, "steps": K,
+           "ms_per_plan": t_dev / K * 1e3, "e2e_ms_per_plan": wall / K * 1e3, "plans_per_s": K / t_dev,
+           "single_gpu_ms": single_ms, "speedup_vs_single_gpu": single_ms / (t_dev / K * 1e3),
+           "exchange": "none (one GPU)" if world == 1 else
+                       "in-kernel stores into the peers' inboxes over NVLink + per-block arrival counters in peer memory",
+           "nvlink_bytes_per_wavefront_per_gpu": None,
+           "plan": {"status": res1.status, "wavefronts": res1.iterations, "edge_checks": res1.edge_pairs,
+                    "route_len": len(single), "pairs_evaluated": res1.edge_evals, "words_swept": res1.word_checks},
+           "identical_tree_on_every_rank": bool(flags.item()),
+           "nccl_allreduce_min_form_ms": nccl_ms if world > 1 else None,
+           "phase_us_per_wavefront_max_over_ranks": dict(zip(("frontier", "select", "connect", "exchange"), (ph_max / wf).tolist())),
+           "phase_us_per_wavefront_min_over_ranks": dict(zip(("frontier", "select", "connect", "exchange"), (ph_min / wf).tolist())),
+           "algorithmic_tflops": res1.edge_pairs * f_edge(m) / (t_dev / K) * 1e-12}
+    # bytes a GPU sends per wavefront: 8 B per candidate node it connected, to each of world-1 peers
+    reached = int(np.sum(np.isfinite(g.dev_cost))) if world > 1 else None
+    if world > 1:
+        rec["nvlink_bytes_per_wavefront_per_gpu"] = 8.0 * (world - 1) * (reached / float(world)) / wf
+        rec["allreduce_bytes_per_wavefront_nccl_form"] = 8.0 * n
+    if rank == 0 and world == 1:
+        save_workload("cfg5", {"n": n, "m": m, "seed": meta["seed"], "start": int(it['start']), "goal": goal,
+                               "edge_pairs": res1.edge_pairs, "wavefronts": res1.iterations, "status": res1.status})
+    del g
+    return rec
+
+
+def run_b200(args):
+    import ctypes as C
+    import multi_gpu
+    import synthetic_world as sw
+    from gmt_planner import GMT
+
+    ctx = Ctx()
+    torch, _lib, lib = ctx.torch, ctx._lib, ctx.lib
+    rank, world, local, dev = ctx.rank, ctx.world, ctx.local, ctx.dev
+    W = max(args.warmup, 3)
+    K = args.steps
+    only = args.only
+    sub = {}
+
+    if only == "cfg4":
+        args.no_sub = True
+    if only and only != "cfg4":                                   # development: one workload, its record as the line
+        if only == "cfg5":
+            rec = time_sharded(ctx)
+        else:
+            rec, _ = time_single(ctx, only, K=max(K, 5), words=args.words, oriented=args.oriented)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "only": only, "value": rec.get("plans_per_s_resident", rec.get("plans_per_s")),
+                              "unit": UNIT, "n_gpus": world, "record": rec}), flush=True)
+        if ctx.dist is not None:
+            ctx.dist.destroy_process_group()
+        return 0
+
+    # ---- headline: cfg4 batch, this rank's share -------------------------------------------------
+    init, it, meta = make_named_world("cfg4", device=local)
+    n, m = meta["n"], meta["m"]
+    g = GMT(init, device=local, words=args.words)
+    ctx.bind(g)
+    obs = np.ascontiguousarray(it['obstacles'], np.float32)
+    _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
+    starts, goals, qcache = batch_queries(g, meta, device=local)              # same list on every rank
+    s, gl = multi_gpu.shard_queries(starts, goals, rank, world)
+    s, gl = np.ascontiguousarray(s, np.int32), np.ascontiguousarray(gl, np.int32)
+    q = len(s)
+    radius, thr0 = float(np.float32(it['radius'])), float(np.float32(it['threshold']))
+    res = (_lib.GmtResult * q)()
+
+    def plan_resident():
+        _lib.check(lib.gmt_plan_queries(g._handle, radius, thr0, 1000, res, None, 0), "gmt_plan_queries")
+
+    def plan_e2e():
+        return sw.plan_batch(g, s, gl, route_stride=ROUTE_STRIDE)          # host arrays in, results + routes out
 
     sampler = ClockSampler(gpu_uuid(torch, dev, local))
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    _lib.check(lib.gmt_set_queries(g._handle, s.ctypes.data, gl.ctypes.data, q), "gmt_set_queries")
+    for _ in range(W):
         plan_resident()
-        g.run_step(it, iter_limit=1000)
+    ctx.barrier()
     sampler.mark()
+    acc = {"kern_ms": 0.0, "launches": 0}
 
-    # ---- value: resident inputs ---------------------------------------------------------------
-    K = args.steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kern_ms, launches, pairs, evals, checks = 0.0, 0, 0, 0, 0
-    barrier()
-    for k in range(K):
-        flush.fill_(k & 0xFF)                                            # evict L2 between timed plans
-        ev[k][0].record(stream)
+    def timed_resident():
         plan_resident()
-        ev[k][1].record(stream)
-        kern_ms += res.device_ms
-        launches += res.launches
-        pairs, evals, checks = res.edge_pairs, res.edge_evals, res.word_checks
-    barrier()
-    t_value = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    status, iterations, goal_cost = res.status, res.iterations, res.goal_cost
+        acc["kern_ms"] += res[0].device_ms
+        acc["launches"] += res[0].launches
+    t_value, _ = ctx.timed(K, timed_resident)
+    ctx.barrier()
+    # self-extend (the same number of extra steps on every rank): a timed region under 0.5 s is too thin for the
+    # clock sampler and for a latency-sensitive kernel
+    (t_slowest,) = multi_gpu.max_over_ranks([t_value], device=dev)
+    extra = 0
+    if t_slowest < 0.5:
+        extra = min(8 * K, K * int(np.ceil(0.5 / max(t_slowest, 1e-6))) - K)
+    if extra > 0:
+        t_more, _ = ctx.timed(extra, timed_resident)
+        t_value += t_more
+        ctx.barrier()
+    K_value = K + extra
+    reached = sum(r.status == 0 for r in res)
+    pairs = sum(r.edge_pairs for r in res)
+    evals = sum(r.edge_evals for r in res)
+    checks = sum(r.word_checks for r in res)
+    per_query_pairs = [int(r.edge_pairs) for r in res]
+    # tail of the batch: when did each team run dry?
+    be = (C.c_ulonglong * (2 * q))()
+    teams = C.c_int()
+    lib.gmt_debug_batch_times(g._handle, be, q, C.byref(teams))
+    ends = np.array(be[1::2], np.float64)
+    begins = np.array(be[0::2], np.float64)
+    busy = float((ends - begins).sum())
+    span = float(ends.max()) if q else 0.0
+    tail = {"teams": teams.value, "queries_per_team": q / float(max(teams.value, 1)),
+            "kernel_span_ms": span * 1e-6, "team_busy_fraction": busy / (span * teams.value) if span else None}
 
-    # ---- e2e: host buffers through GMT.run_step -------------------------------------------------
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    wall = 0.0
-    barrier()
-    for k in range(K):
-        flush.fill_(k & 0xFF)
-        torch.cuda.synchronize(dev)
-        ev2[k][0].record(stream)
-        t0 = time.perf_counter()
-        route = g.run_step(it, iter_limit=1000)
-        wall += time.perf_counter() - t0
-        ev2[k][1].record(stream)
-        launches += g.last_result.launches
-    barrier()
-    t_e2e = max(sum(a.elapsed_time(b) for a, b in ev2) * 1e-3, wall)
+    for _ in range(2):
+        plan_e2e()
+    ctx.barrier()
+    e2e_launch = {"n": 0}
+
+    def timed_e2e():
+        r_, _routes = plan_e2e()
+        e2e_launch["n"] += r_[0].launches
+    _, t_e2e = ctx.timed(K, timed_e2e)
     clocks = sampler.stop()
+    ctx.barrier()
+    t_value_pr, t_e2e_pr = t_value / K_value, t_e2e / K                   # per step, this rank
+    t_value_pr, t_e2e_pr, kern_ms = multi_gpu.max_over_ranks([t_value_pr, t_e2e_pr, acc["kern_ms"] / K_value], device=dev)
+    tot = torch.tensor([pairs, evals, checks, reached], dtype=torch.float64, device=dev)
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(tot)
+    pairs_all, evals_all, checks_all, reached_all = (float(v) for v in tot.cpu())
+    assert kern_ms <= t_value_pr * 1e3 * 1.0005 + 1e-3, "kernel time %.3f ms exceeds the step time %.3f ms" % (kern_ms, t_value_pr * 1e3)
 
-    import multi_gpu
-    t_value, t_e2e = multi_gpu.max_over_ranks([t_value, t_e2e], device=dev)     # slowest rank
-
-    # ---- edge kernel in isolation (the "Dubins edge checks/sec" half of the metric) -------------
-    edge = None
+    # ---- sub-records ---------------------------------------------------------------------------
     fp32_peak = C.c_float()
-    if rank == 0:
-        _lib.check(lib.gmt_measure_fp32_peak(local, C.byref(fp32_peak)), "gmt_measure_fp32_peak")
+    _lib.check(lib.gmt_measure_fp32_peak(local, C.byref(fp32_peak)), "gmt_measure_fp32_peak")
+    edge = None
+    if world == 1 and not args.no_sub:
+        # edge kernel in isolation (the "Dubins edge checks/sec" half of the metric)
         rng = np.random.default_rng(7)
         P = 1 << 18
         nbr, num = init['neighbors'], init['num_neighbors']
@@ -337,46 +718,65 @@ def run_b200(args):
                                           C.byref(ms)), "gmt_edge_costs")
             best_ms = min(best_ms, ms.value)
         edge = {"pairs": P, "ms": best_ms, "edge_checks_per_s": P / (best_ms * 1e-3),
-                "what": "all 4 words + swept-path test of neighbour pairs, no pruning"}
+                "what": "all %d words + swept-path test of neighbour pairs, no pruning (gmt_edge_costs_kernel)" % args.words,
+                "fp32_frac": P / (best_ms * 1e-3) * f_edge(m) * 1e-12 / fp32_peak.value,
+                "ncu": profile_json("ncu_summary.json").get("gmt_edge_costs_kernel")}
+        for name in ("cfg2", "cfg3", "cfg3u"):
+            try:
+                rec, keep = time_single(ctx, name, K=30, words=args.words, oriented=args.oriented)
+                if name == "cfg2" and args.words == 4 and not args.oriented:
+                    rec["gpu_reference"] = gpu_reference_leg(ctx, keep[0], keep[1], keep[2], "cfg2 query")
+                sub[name] = rec
+                del keep
+            except Exception as e:          # a sub-record must never take the headline down
+                sub[name] = {"failed": repr(e)}
+    if not args.no_sub:
+        try:
+            sub["cfg5"] = time_sharded(ctx)
+        except Exception as e:
+            sub["cfg5"] = {"failed": repr(e)}
+            ctx.barrier()
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if ctx.dist is not None:
+            ctx.dist.destroy_process_group()
         return 0
 
-    value = world * K / t_value
-    e2e_value = world * K / t_e2e
-    kern_s = kern_ms * 1e-3 / K
-    achieved = pairs * f_edge(m) / kern_s * 1e-12
+    value = Q_BATCH / t_value_pr
+    e2e_value = Q_BATCH / t_e2e_pr
+    kern_s = kern_ms * 1e-3
+    achieved = pairs_all / world * f_edge(m) / kern_s * 1e-12              # per GPU: its share of the work / its kernel time
+    executed = f_executed(evals_all / world, checks_all / world, args.words) / kern_s * 1e-12
+    ncu = profile_json("ncu_summary.json")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-        "ms_per_step": t_value / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "n": n, "m": m, "seed": meta["seed"],
-                   "mean_degree": round(meta["mean_degree"], 2), "queries_per_step_per_gpu": 1,
-                   "multi_gpu": "each rank plans this query independently on its own replica (no collective)",
-                   "l2": "flushed between timed plans (256 MiB fill)", "iter_limit": 1000,
-                   "plan": {"status": status, "wavefronts": iterations, "goal_cost": goal_cost,
-                            "route_len": len(route), "edge_checks": pairs, "pairs_evaluated": evals,
-                            "words_swept": checks}},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(16 * m),
-                "d2h_bytes_per_step": int(512 + 4 * min(n + 1, 1024)), "ms_per_step": t_e2e / K * 1e3},
-        "gpu_launches": launches,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_value_pr * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": headline_config(),
+        "timing": {"timed_steps_value": K_value, "l2": "flushed before every timed step (256 MiB fill on the timing stream)",
+                   "stream": "explicit torch stream handed to the library (gmt_set_stream)",
+                   "queries_per_rank": q, "kernel_ms_per_step": kern_ms,
+                   "mean_degree": round(meta["mean_degree"], 2), "words": args.words},
+        "batch": {"goal_reached": int(reached_all), "edge_checks": int(pairs_all), "pairs_evaluated": int(evals_all),
+                  "words_swept": int(checks_all), "tail_rank0": tail},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * q),
+                "d2h_bytes_per_step": int(q * (C.sizeof(_lib.GmtResult) + 4 * ROUTE_STRIDE)), "ms_per_step": t_e2e_pr * 1e3,
+                "note": "gmt_plan_batch: host start/goal arrays in, host result structs + routes out, wall clock"},
+        "gpu_launches": acc["launches"] + e2e_launch["n"],
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"]},
-        "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "achieved": achieved, "peak": fp32_peak.value,
-                     "unit": "TFLOP/s", "frac": achieved / fp32_peak.value if fp32_peak.value else None,
-                     "traffic": workload_meta(args.config).get("ncu_dram_bytes_per_launch"), "kernel_ms": kern_s * 1e3,
-                     "note": "achieved = reference edge checks (sum |X|*|Y| = %d) x F_edge(m=%d) = %.0f op/check "
-                             "/ kernel time; peak = FP32 FMA micro-benchmark measured live on this GPU "
-                             "(MEASURED_PEAKS.json has no FP32 figure). >1 is expected: exact pruning evaluates "
-                             "%d of those pairs and sweeps %d words" % (pairs, m, f_edge(m), evals, checks)},
+        "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel<4,false,512> (team mode)", "achieved": achieved,
+                     "peak": fp32_peak.value, "unit": "TFLOP/s", "frac": achieved / fp32_peak.value if fp32_peak.value else None,
+                     "executed": executed, "executed_frac": executed / fp32_peak.value if fp32_peak.value else None,
+                     "traffic": (ncu.get("gmt_plan_kernel_batch") or {}).get("dram_bytes_per_launch"),
+                     "kernel_ms": kern_ms, "ncu": ncu.get("gmt_plan_kernel_batch"),
+                     "peak_source": "FP32 FMA micro-benchmark measured live on this GPU (MEASURED_PEAKS.json has no FP32 figure)",
+                     "note": "achieved = reference edge checks (sum |X|*|Y| over the batch = %d per GPU) x F_edge(m=%d) = %.0f "
+                             "op/check / kernel time: > 1 because exact pruning evaluates %d of those pairs and sweeps %d "
+                             "words; executed = op-equivalents of the work actually done; ncu = pipe utilisation of the "
+                             "committed capture of this launch" % (pairs_all / world, m, f_edge(m), evals_all / world, checks_all / world)},
         "edge_kernel": edge,
+        "sub": sub,
     }
-    if edge:
-        line["edge_kernel"]["fp32_frac"] = edge["edge_checks_per_s"] * f_edge(m) * 1e-12 / fp32_peak.value
-    # the HBM view of the same kernel, for completeness: measured DRAM bytes per launch (ncu) over its duration
-    # against the measured copy bandwidth of MEASURED_PEAKS.json -- it shows how far from memory-bound the path is
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
@@ -385,260 +785,46 @@ def run_b200(args):
     line["roofline"]["hbm"] = {"achieved": (traffic / kern_s * 1e-9) if traffic else None, "peak": hbm_peak, "unit": "GB/s",
                                "frac": (traffic / kern_s * 1e-9 / hbm_peak) if traffic and hbm_peak else None,
                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "absent"}
-    out_dir = os.path.join(ROOT, "gpurun_out")
-    if os.path.isdir(out_dir):          # workload facts to cache under profiles/ (committed by hand)
-        with open(os.path.join(out_dir, "workload_cfg%d.json" % args.config), "w") as f:
-            json.dump({"n": n, "m": m, "seed": meta["seed"], "start": start, "goal": goal, "edge_pairs": pairs,
-                       "wavefronts": iterations, "status": status, "goal_cost": goal_cost}, f)
+    if world == 1:
+        save_workload("cfg4", {"n": n, "m": m, "seed": meta["seed"], "starts": [int(v) for v in starts],
+                               "goals": [int(v) for v in goals], "edge_pairs": per_query_pairs})
 
     # ---- cpu baseline (rank 0, N = 1 only) -------------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
         try:
-            backend, kind, cores = cpu_backend()
-            init_c, it_c, _ = cpu_world(args.config)
-            v, desc = cpu_sample(init_c, it_c, backend, args.cpu_budget, pairs)
+            cores = host_cores()
+            backend, kind = cpu_backend()
+            init_c, it_c, _ = make_named_world("cfg4", cpu=True)
+            v, desc = cpu_batch_sample(init_c, it_c, backend, starts, goals, per_query_pairs, 0, cores, args.cpu_budget, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+            line["cpu_edge_checks"] = {
+                "all_cores": {"edge_checks_per_s": cpu_edge_checks(init_c, it_c, backend, 100000, cores), "pairs": 100000, "cores": cores},
+                "one_core": {"edge_checks_per_s": cpu_edge_checks(init_c, it_c, backend, 20000, 1), "pairs": 20000, "cores": 1},
+                "what": "computeDubinsCost of the reference (kernel.py:418-431) on neighbour pairs of the cfg4 map, m = %d" % m}
         except Exception as e:  # the baseline must never take the measurement down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (e,)}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
-
-
-def run_b200_batch(args):
-    """BASELINE config 4: 4096 independent queries on one 10k map; each rank plans its contiguous share
-    with gmt_plan_batch (one launch, teams of blocks); strong scaling, no collective on the data path."""
-    import ctypes as C
-
-    import torch
-    import _lib
-    import multi_gpu
-    import synthetic_world as sw
-    from gmt_planner import GMT
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the planner has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = _lib.load()
-    dev = torch.device("cuda", local)
-    Q = 4096
-    init, it, meta = sw.make_world(4)
-    n, m = meta["n"], meta["m"]
-    g = GMT(init, device=local)
-    stream = torch.cuda.current_stream(dev)
-    _lib.check(lib.gmt_set_stream(g._handle, C.c_void_p(stream.cuda_stream)), "gmt_set_stream")
-    obs = np.ascontiguousarray(it['obstacles'], np.float32)
-    _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")
-    starts, goals = sw.make_reachable_queries(g, n, Q, meta["seed"] + 7)       # same list on every rank
-    s, gl = multi_gpu.shard_queries(starts, goals, rank, world)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(gpu_uuid(torch, dev, local))
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        res, _r = sw.plan_batch(g, s, gl)
-    sampler.mark()
-    K = args.steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches, kern_ms = 0, 0.0
-    barrier()
-    for k in range(K):
-        flush.fill_(k & 0xFF)
-        ev[k][0].record(stream)
-        res, routes = sw.plan_batch(g, s, gl, route_stride=128)      # host buffers in, results + routes out
-        ev[k][1].record(stream)
-        launches += res[0].launches
-        kern_ms += res[0].device_ms
-    barrier()
-    t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    clocks = sampler.stop()
-    (t,) = multi_gpu.max_over_ranks([t], device=dev)
-    reached = sum(r.status == 0 for r in res)
-    pairs = sum(r.edge_pairs for r in res)
-    if rank == 0:
-        value = Q * K / t
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-                "warmup": max(args.warmup, 3), "ms_per_step": t / K * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOADS[4], "n": n, "m": m, "seed": meta["seed"], "queries": Q,
-                           "queries_per_rank": len(s), "l2": "flushed between timed batches (256 MiB fill)",
-                           "goal_reached_rank0": reached, "edge_checks_rank0": pairs},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * len(s)),
-                        "d2h_bytes_per_step": int(len(s) * (144 + 4 * 128)),
-                        "note": "the batch call takes host start/goal arrays and returns host results + routes: value is e2e"},
-                "gpu_launches": launches,
-                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                           "samples": clocks["samples"]},
-                "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "unit": "TFLOP/s", "traffic": None,
-                             "achieved": pairs * f_edge(m) / (kern_ms / K * 1e-3) * 1e-12, "peak": None, "frac": None,
-                             "kernel_ms": kern_ms / K}}
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
-
-
-def run_b200_sharded(args):
-    """BASELINE config 5: ONE plan on a 1M-sample roadmap, every GPU connects the candidate nodes of its node
-    range.  N = 1: the plain persistent plan.  N > 1: the fused form (one launch per GPU, the per-wavefront
-    exchange goes over NVLink peer memory inside the kernel); the NCCL all-reduce(min) form is timed beside it.
-    Strong scaling: value = plans/s of the one plan all GPUs work on."""
-    import ctypes as C
-
-    import torch
-    import _lib
-    import multi_gpu
-    import synthetic_world as sw
-    from gmt_planner import GMT
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the planner has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = _lib.load()
-    dev = torch.device("cuda", local)
-    init, it, meta = sw.make_world(5, sampler=lambda *a: sw.cuda_sampler(*a, device=local),
-                                   neighbor_builder=lambda s_, r_: sw.cuda_neighbor_builder(s_, r_, device=local))
-    n, m = meta["n"], meta["m"]
-    cached = workload_meta(5)
-    if cached.get("n") == n and cached.get("seed") == meta["seed"] and cached.get("start") == int(it['start']):
-        goal = int(cached["goal"])
-    else:
-        goal = sw.pick_reachable_goal(init, it, meta["side"], explore=lambda a, b: sw.explore_cuda(a, b, device=local)) \
-            if rank == 0 else 0
-        gt = torch.tensor([goal], device=dev)
-        if dist is not None:
-            dist.broadcast(gt, 0)
-        goal = int(gt.item())
-    it = dict(it, goal=goal)
-    g = GMT(init, device=local)
-    stream = torch.cuda.current_stream(dev)
-    _lib.check(lib.gmt_set_stream(g._handle, C.c_void_p(stream.cuda_stream)), "gmt_set_stream")
-    single = list(g.run_step(it, iter_limit=1000))                   # also the check value for the sharded forms
-    res1 = g.last_result
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    if world > 1:
-        multi_gpu.open_peers(g, rank, world)
-
-        def step():
-            return multi_gpu.run_step_sharded_p2p(g, it, iter_limit=1000, rank=rank, world=world)
-    else:
-        def step():
-            return g.run_step(it, iter_limit=1000), g.last_result
-    sampler = ClockSampler(gpu_uuid(torch, dev, local))
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        route, res = step()
-    sampler.mark()
-    K = args.steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches = 0
-    barrier()
-    for k in range(K):
-        flush.fill_(k & 0xFF)
-        ev[k][0].record(stream)
-        route, res = step()
-        ev[k][1].record(stream)
-        launches += res.launches
-    barrier()
-    t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    clocks = sampler.stop()
-    same = int(list(route) == single)
-    nccl_ms = None
-    if world > 1:
-        multi_gpu.close_peers(g)
-        barrier()
-        t0 = time.perf_counter()
-        r2, _res2, steps2 = multi_gpu.run_step_sharded(g, it, iter_limit=1000, rank=rank, world=world)
-        torch.cuda.synchronize(dev)
-        nccl_ms = (time.perf_counter() - t0) * 1e3
-        same = int(same and list(r2) == single)
-    t, nccl_ms_max = multi_gpu.max_over_ranks([t, nccl_ms or 0.0], device=dev)
-    flags = torch.tensor([same], device=dev)
-    if dist is not None:
-        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        value = K / t
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-                "warmup": max(args.warmup, 3), "ms_per_step": t / K * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOADS[5], "n": n, "m": m, "seed": meta["seed"],
-                           "l2": "flushed between timed plans (256 MiB fill)",
-                           "exchange": "none (one GPU)" if world == 1 else
-                                       "in-kernel stores into the peers' arrays over NVLink + flag barrier in peer memory",
-                           "plan": {"status": res1.status, "wavefronts": res1.iterations, "edge_checks": res1.edge_pairs,
-                                    "route_len": len(single), "single_gpu_ms": res1.device_ms},
-                           "identical_tree_on_every_rank": bool(flags.item()),
-                           "nccl_allreduce_min_path_ms": nccl_ms_max if world > 1 else None},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(16 * m),
-                        "d2h_bytes_per_step": int(512 + 4 * min(n + 1, 1024)),
-                        "note": "timed through GMT.run_step / multi_gpu.run_step_sharded_p2p with host obstacle arrays"},
-                "gpu_launches": launches,
-                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                           "samples": clocks["samples"]},
-                "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel", "unit": "TFLOP/s", "traffic": None,
-                             "achieved": res1.edge_pairs * f_edge(m) / (t / K) * 1e-12, "peak": None, "frac": None,
-                             "note": "algorithmic op count of the reference formulation (SURVEY 8d); exact pruning "
-                                     "skips almost all of it, see profiles/ for the issue-slot utilisation"}}
-        print(json.dumps(line), flush=True)
-        out_dir = os.path.join(ROOT, "gpurun_out")
-        if os.path.isdir(out_dir):
-            with open(os.path.join(out_dir, "workload_cfg5.json"), "w") as f:
-                json.dump({"n": n, "m": m, "seed": meta["seed"], "start": int(it['start']), "goal": goal,
-                           "edge_pairs": res1.edge_pairs, "wavefronts": res1.iterations, "status": res1.status}, f)
-    if dist is not None:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS))
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU dubinConnection work per sample")
+    ap.add_argument("--only", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--words", type=int, default=4, choices=[4, 6], help="6: also RLR / LRL (extension mode, parity unpinned)")
+    ap.add_argument("--oriented", action="store_true", help="single-query sub-records on oriented rectangles (extension mode)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU dubinConnection work per sampled plan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline only")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.config in (4, 5):
-            args.config = 2          # the CPU arm times one query of the same kind of map
         return run_reference(args)
-    if args.config == 4:
-        if args.steps == 200:
-            args.steps = 5
-        return run_b200_batch(args)
-    if args.config == 5:
-        if args.steps == 200:
-            args.steps = 10
-        return run_b200_sharded(args)
     return run_b200(args)
 
 

@@ -57,6 +57,9 @@ PROTOTYPES = {
     "gmt_peer_open": (_i, [_vp, _i, _i, _vp]),
     "gmt_peer_close": (_i, [_vp]),
     "gmt_plan_sharded_p2p": (_i, [_vp, _i, _i, _f, _f, _i, _i, _i, C.POINTER(GmtResult)]),
+    "gmt_set_queries": (_i, [_vp, _vp, _vp, _i]),
+    "gmt_plan_queries": (_i, [_vp, _f, _f, _i, _vp, _vp, _i]),
+    "gmt_debug_batch_times": (_i, [_vp, _vp, _i, _vp]),
     "gmt_set_option": (_i, [_vp, C.c_char_p, _i]),
     "gmt_debug_barrier_us": (_i, [_vp, _i, _i, _i, _fp]),
     "gmt_debug_counters": (_i, [_vp, _vp]),

@@ -95,10 +95,16 @@ def unpack_keys(keys):
 
 
 def allreduce_min(t):
-    """The per-wavefront exchange: NCCL all-reduce(min) of the packed cost/parent array over NVLink."""
+    """The per-wavefront exchange: NCCL all-reduce(min) of the packed cost/parent array over NVLink.
+    Returns only when the reduction has COMPLETED on the device: the next gmt_sharded_step launches on the
+    handle's own stream, which has no dependency on the stream the collective ran on (include/gmt_c_api.h,
+    "STREAM ORDERING")."""
+    import torch
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
 
 
 def run_step_sharded(gmt, iter_parameters, iter_limit=1000, rank=0, world=1, exchange=allreduce_min):

@@ -24,7 +24,7 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "gmt_plans_per_sec" and d["unit"] == "plans/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
-    assert d["config"]["workload"].startswith("cfg2")
+    assert d["config"]["workload"].startswith("cfg4") and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

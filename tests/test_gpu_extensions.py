@@ -84,8 +84,10 @@ def test_edge_kernel_extension_modes_match_oracle(gmt_lib, ext, words, oriented)
            "oracle: %d (max %d ulp); verdict words differing: %d; colliding words: %d"
            % (words, oriented, P, n_ccc, int((ulp > 0).sum()), int(ulp.max()), int((bits != obits).sum()),
               int(sum(bin(int(v) >> cb).count("1") for v in bits))))
-    assert np.mean(ulp > 4) < 2e-3
-    assert np.mean(bits != obits) < 2e-3
+    # extension mode has no reference pin (the C restatement is its definition, evaluated with glibc-emulating
+    # arithmetic): verdicts must be identical; lengths may differ by 1 ulp on a handful of words (logged above)
+    assert int(ulp.max()) <= 1 and int((ulp > 0).sum()) <= 32
+    assert int((bits != obits).sum()) == 0
     same = bits == obits
     assert np.array_equal(best[same].view(np.uint32), obest[same].view(np.uint32)) or \
         np.mean(np.abs(best[same] - obest[same]) > RTOL * np.abs(obest[same])) < 2e-3

@@ -129,8 +129,10 @@ def test_edge_kernel_matches_golden_and_oracle(gmt_lib, oracles, tag):
     ulp = _ulp_diff(cost4[ok], o4[ok])
     report("edge %s: cost words differing from cuda-flavour oracle: %d of %d (max %d ulp); verdict words differing: %d"
           % (tag, int((ulp > 0).sum()), int(ok.sum()), int(ulp.max()), int((bits != obits).sum())))
-    assert np.mean(ulp > 4) < 2e-3
-    assert np.mean(bits != obits) < 2e-3                # boundary cases only (logged above)
+    # north star: bit-exact; a boundary case (sample point within eps of a box edge, or the one hardware-defined
+    # instruction of powf) would be LOGGED above and fail here -- none has ever been observed
+    assert int((ulp > 0).sum()) == 0
+    assert int((bits != obits).sum()) == 0
     # against the reference-source golden (glibc math): 1e-5 relative except wrap flips
     gold = e["cost4_bits"].view(np.float32)
     assert np.array_equal(np.isnan(cost4), np.isnan(gold))
@@ -180,12 +182,13 @@ def _compare_plan(g, ref_status, ref_iters, ref_parent, ref_cost, ref_trace, sta
         return
     np.testing.assert_allclose(cost[fin], ref_cost[fin], rtol=RTOL, err_msg=tag)
     diff = np.flatnonzero(parent != ref_parent)
-    # a parent may differ from the CPU oracle only where two candidates tie to within rounding
-    for i in diff:
-        assert abs(cost[i] - ref_cost[i]) <= RTOL * max(1.0, abs(ref_cost[i])), (tag, int(i))
-    report("%s: %d parents differ from the CPU oracle (ties within %g), of %d connected"
-          % (tag, len(diff), RTOL, int(fin.sum())))
-    assert len(diff) <= max(2, int(0.002 * fin.sum())), tag
+    # north star: tree parents bit-exact.  Every differing node is logged with both costs (an eps-tie between two
+    # candidates would show here) and fails the test: zero tolerance
+    for i in diff[:20]:
+        report("%s: node %d parent %d (cost %.9g) vs oracle parent %d (cost %.9g)"
+               % (tag, int(i), int(parent[i]), float(cost[i]), int(ref_parent[i]), float(ref_cost[i])))
+    report("%s: %d parents differ from the CPU oracle, of %d connected" % (tag, len(diff), int(fin.sum())))
+    assert len(diff) == 0, tag
 
 
 @pytest.mark.parametrize("n,m,seed,mode", [(2000, 20, 19, "uniform"), (1200, 0, 5, "uniform"),
@@ -352,6 +355,70 @@ def test_full_size_plan_properties(GMT, gmt_lib, config):
         assert (best < 1e9).all()
     report("config %d: status %d, %d iterations, %.3f ms on device, %d edge pairs, %d evaluated, %d swept"
           % (config, g.status, g.iterations, res.device_ms, res.edge_pairs, res.edge_evals, res.word_checks))
+
+
+def _bench_world(name):
+    """The very world and query bench.py measures (bench.make_named_world + bench_query, cached goal)."""
+    import bench
+    init, it, meta = bench.make_named_world(name)
+    it, _ = bench.bench_query(name, init, it, meta)
+    return init, it, meta
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_full_size_plan_bit_exact_vs_reference_kernels(GMT, refgpu, name):
+    """BASELINE cfg2 (10k / 100 boxes) and cfg3 (100k / 2k boxes on streets) -- the worlds and queries of bench.py --
+    planned by the CUDA path and by the reference's own kernels on this GPU (device-resident restated loop):
+    status, iteration count, EVERY parent and EVERY cost bit pattern equal; goal cost within 1e-5 (it is equal)."""
+    from oracle.ref_gpu import RefGpuPlanner
+    init, it, meta = _bench_world(name)
+    r = RefGpuPlanner(init, refgpu).run_step(it, iter_limit=1000)
+    g = GMT(init)
+    route = g.run_step(it, iter_limit=1000)
+    assert (g.status, g.iterations) == (r["status"], r["iterations"])
+    dp = int((g.parent != r["parent"]).sum())
+    dc = int((g.dev_cost.view(np.uint32) != r["cost"].view(np.uint32)).sum())
+    report("%s whole plan vs reference kernels on this GPU: status %d, %d wavefronts, %d edge checks, %d nodes connected; "
+           "parents differing %d, cost bit patterns differing %d (reference: %.2f s, CUDA path: %.3f ms)"
+           % (name, g.status, g.iterations, r["edge_pairs"], int((r["parent"] >= 0).sum()), dp, dc, r["seconds"],
+              g.last_result.device_ms))
+    assert dp == 0 and dc == 0
+    assert list(route) == r["route"]
+    assert g.last_result.edge_pairs == r["edge_pairs"]
+    gc, rc = float(g.dev_cost[it['goal']]), float(r["cost"][it['goal']])
+    assert abs(gc - rc) <= RTOL * rc
+
+
+def test_cfg4_queries_bit_exact_vs_reference_kernels(GMT, gmt_lib, refgpu):
+    """32 queries of BASELINE cfg4 (the batch bench.py times): the batched launch gives every query the route, status,
+    iteration count and goal cost of a single plan, and 6 of them are checked, parents and cost bits, against the
+    reference's own kernels on this GPU."""
+    import bench
+    import synthetic_world as sw
+    from oracle.ref_gpu import RefGpuPlanner
+    init, it, meta = bench.make_named_world("cfg4")
+    g = GMT(init)
+    g.set_obstacles(it['obstacles'], it['num_obs'])
+    starts, goals, _ = bench.batch_queries(g, meta)
+    sel = np.linspace(0, len(starts) - 1, 32).astype(int)
+    s, gl = starts[sel], goals[sel]
+    res, routes = sw.plan_batch(g, s, gl, route_stride=512)
+    ref = RefGpuPlanner(init, refgpu)
+    single = GMT(init)
+    for k in range(32):
+        q = dict(it, start=int(s[k]), goal=int(gl[k]))
+        route = list(single.run_step(q, iter_limit=1000))
+        assert (res[k].status, res[k].iterations, res[k].route_len) == (single.status, single.iterations, len(route)), k
+        assert list(routes[k][:len(route)]) == route[:512], k
+        assert np.float32(res[k].goal_cost).view(np.uint32) == np.float32(single.last_result.goal_cost).view(np.uint32)
+        if k % 6 == 0:
+            r = ref.run_step(q, iter_limit=1000)
+            assert (single.status, single.iterations) == (r["status"], r["iterations"]), k
+            assert np.array_equal(single.parent, r["parent"]), k
+            assert np.array_equal(single.dev_cost.view(np.uint32), r["cost"].view(np.uint32)), k
+            assert route == r["route"], k
+    report("cfg4: 32 batched queries == single plans (route, status, iterations, goal-cost bits); 6 of them bit-identical "
+           "(parents, cost patterns) to the reference kernels on this GPU")
 
 
 def test_resident_obstacles_give_the_same_plan(GMT, gmt_lib):
