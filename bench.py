@@ -184,7 +184,7 @@ def host_cores():
 # --------------------------------------------------------------------------------------------------
 # worlds
 # --------------------------------------------------------------------------------------------------
-def make_named_world(name, cpu=False, device=0):
+def make_named_world(name, cpu=False, device=0, with_neighbors=True):
     """(init, it, meta) of a named workload; cpu=True builds it with the NumPy restatements (bit-identical to the
     CUDA builders, tests/test_world_oracle.py + tests/test_gpu_parity.py) so that the CPU arm needs no GPU."""
     import synthetic_world as sw
@@ -195,6 +195,7 @@ def make_named_world(name, cpu=False, device=0):
     else:
         kw = dict(sampler=lambda *a: sw.cuda_sampler(*a, device=device),
                   neighbor_builder=lambda s_, r_: sw.cuda_neighbor_builder(s_, r_, device=device))
+    kw["with_neighbors"] = with_neighbors
     if name == "cfg3u":
         return sw.make_world(n=100000, m=500, seed=31, mode="uniform", layout="uniform", **kw)
     if name == "cfg4":
@@ -513,19 +514,23 @@ def time_sharded(ctx, K=8):
     from gmt_planner import GMT
     torch, _lib, lib = ctx.torch, ctx._lib, ctx.lib
     rank, world = ctx.rank, ctx.world
-    init, it, meta = make_named_world("cfg5", device=ctx.local)
+    init, it, meta = make_named_world("cfg5", device=ctx.local, with_neighbors=False)   # lists are built on the device
     n, m = meta["n"], meta["m"]
     goal, cache = cached_goal("cfg5", it, meta)
     if goal is None:
         if rank == 0:
-            it2, cache = bench_query("cfg5", init, it, meta, device=ctx.local)
+            init_full, _it, _meta = make_named_world("cfg5", device=ctx.local)
+            it2, cache = bench_query("cfg5", init_full, it, meta, device=ctx.local)
             goal = int(it2['goal'])
+            del init_full
         gt = torch.tensor([goal or 0], device=ctx.dev)
         if ctx.dist is not None:
             ctx.dist.broadcast(gt, 0)
         goal = int(gt.item())
     it = dict(it, goal=goal)
-    g = GMT(init, device=ctx.local)
+    t0 = time.perf_counter()
+    g = GMT.from_states(init['states'], device=ctx.local)
+    create_ms = (time.perf_counter() - t0) * 1e3
     ctx.bind(g)
     with torch.cuda.stream(ctx.stream):
         single = list(g.run_step(it, iter_limit=1000))                   # also the check value for the sharded forms
@@ -573,7 +578,7 @@ def time_sharded(ctx, K=8):
     wf = max(res1.iterations, 1)
     rec = {"workload": WORKLOADS["cfg5"], "n": n, "m": m, "seed": meta["seed"], "n_gpus": world, "steps": K,
            "ms_per_plan": t_dev / K * 1e3, "e2e_ms_per_plan": wall / K * 1e3, "plans_per_s": K / t_dev,
-           "single_gpu_ms": single_ms, "speedup_vs_single_gpu": single_ms / (t_dev / K * 1e3),
+           "roadmap_build_ms": create_ms, "single_gpu_ms": single_ms, "speedup_vs_single_gpu": single_ms / (t_dev / K * 1e3),
            "exchange": "none (one GPU)" if world == 1 else
                        "in-kernel stores into the peers' inboxes over NVLink + per-block arrival counters in peer memory",
            "nvlink_bytes_per_wavefront_per_gpu": None,

@@ -57,6 +57,10 @@ PROTOTYPES = {
     "gmt_peer_open": (_i, [_vp, _i, _i, _vp]),
     "gmt_peer_close": (_i, [_vp]),
     "gmt_plan_sharded_p2p": (_i, [_vp, _i, _i, _f, _f, _i, _i, _i, C.POINTER(GmtResult)]),
+    "gmt_create_from_states": (_i, [_vp, _i, C.c_double, _i, C.POINTER(_vp)]),
+    "gmt_get_neighbors": (_i, [_vp, _vp, _vp, C.c_longlong, _vp]),
+    "gmt_set_obstacles_from_vehicles": (_i, [_vp, _vp, _i, C.c_double, C.c_double, C.c_double, C.c_double, _i, _vp]),
+    "gmt_get_obstacles": (_i, [_vp, _vp, _vp, _i, _vp]),
     "gmt_set_queries": (_i, [_vp, _vp, _vp, _i]),
     "gmt_plan_queries": (_i, [_vp, _f, _f, _i, _vp, _vp, _i]),
     "gmt_debug_batch_times": (_i, [_vp, _vp, _i, _vp]),

@@ -158,12 +158,36 @@ __global__ void cell_scatter_kernel(const float *__restrict__ xyt, int n, const 
     sorted[pos] = make_float4(xyt[3 * i], xyt[3 * i + 1], __int_as_float(i), 0.f);   // SoA-style float4 record
 }
 
-__device__ __forceinline__ bool is_neighbour(float xi, float yi, float4 c, double r)
+// The rule is (double)sqrtf(q) <= r with q = fl(fl(dx*dx) + fl(dy*dy)).  sqrtf is monotone, so it is the same as
+// q <= qmax where qmax is the LARGEST float whose square root passes (found on the host by bisection over the float
+// bit patterns, q_threshold below): one compare instead of a square root, a conversion and a double compare.
+__device__ __forceinline__ bool is_neighbour(float xi, float yi, float4 c, float qmax)
 {
     if (c.x == xi && c.y == yi) return false;                     // same location (cuda_agent.py:78)
     const float dx = __fsub_rn(xi, c.x), dy = __fsub_rn(yi, c.y);
-    const float d = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-    return (double)d <= r;                                        // inclusive (cuda_agent.py:80)
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= qmax;   // inclusive (cuda_agent.py:80)
+}
+
+// bitonic sort of up to 64 ints held two per lane (slot = lane + 32 * half), ascending; pads are INT_MAX
+__device__ __forceinline__ void warp_sort64(int &a, int &b, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            if (j == 32) {                                        // partner = the other half, same lane (k = 64: ascending)
+                const int lo = min(a, b), hi = max(a, b);
+                a = lo; b = hi;
+            } else {
+                const int pa = __shfl_xor_sync(0xffffffffu, a, j), pb = __shfl_xor_sync(0xffffffffu, b, j);
+                const bool lower = (lane & j) == 0;               // I hold the lower slot of the pair
+                const bool up_a = (lane & k) == 0 || k == 64;     // slots 0..31: bit k of the slot = bit k of the lane
+                const bool up_b = ((lane + 32) & k) == 0;         // slots 32..63
+                a = (lower == up_a) ? min(a, pa) : max(a, pa);
+                b = (lower == up_b) ? min(b, pb) : max(b, pb);
+            }
+        }
+    }
 }
 
 // pass 0: count row lengths; pass 1: write the rows, ascending.  One WARP per state, states taken in cell order
@@ -175,7 +199,7 @@ __device__ __forceinline__ bool is_neighbour(float xi, float yi, float4 c, doubl
 #define NBR_WARPS 8
 #define ROW_SMEM 256
 template <int kPass>
-__global__ void __launch_bounds__(NBR_WARPS * 32) neighbour_kernel(int n, CellGrid g, double r,
+__global__ void __launch_bounds__(NBR_WARPS * 32) neighbour_kernel(int n, CellGrid g, float r,
                                  const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                  int *row_cnt_or_off, int *vals)
 {
@@ -208,6 +232,13 @@ __global__ void __launch_bounds__(NBR_WARPS * 32) neighbour_kernel(int n, CellGr
     if (!kPass) { if (lane == 0) row_cnt_or_off[i] = cnt; return; }
     int *row = vals + row_cnt_or_off[i];
     __syncwarp();
+    if (cnt <= 64) {                                               // the usual row (~55 entries): sort in registers
+        int a = lane < cnt ? s_row[wib][lane] : 0x7fffffff, b = lane + 32 < cnt ? s_row[wib][lane + 32] : 0x7fffffff;
+        warp_sort64(a, b, lane);
+        if (lane < cnt) row[lane] = a;
+        if (lane + 32 < cnt) row[lane + 32] = b;
+        return;
+    }
     if (cnt <= ROW_SMEM) {
         for (int a = lane; a < cnt; a += 32) {
             const int v = s_row[wib][a];
@@ -255,19 +286,30 @@ int gmt_sample_states(unsigned seed, int n, float side, int mode, int device, fl
     return GMT_OK;
 }
 
-int gmt_build_neighbors(const float *states_xyt, int n, double disk_radius, int device, int **vals, int **counts,
-                        long long *total)
+// largest float q with (double)sqrtf(q) <= r (r >= 0): bisection over the bit patterns of the non-negative floats
+static float q_threshold(double r)
 {
-    if (!states_xyt || n <= 0 || !vals || !counts || !(disk_radius >= 0.0)) return GMT_ERR_INVALID;
-    *vals = nullptr; *counts = nullptr;
-    if (total) *total = 0;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return GMT_ERR_CUDA;
-    RCK(cudaSetDevice(device));
+    unsigned lo = 0u, hi = 0x7f7fffffu;                           // invariant: pattern lo passes
+    if ((double)sqrtf(0.0f) > r) return -1.0f;                    // (r < 0 is rejected by the caller)
+    while (lo < hi) {
+        const unsigned mid = lo + (hi - lo + 1u) / 2u;
+        float q; memcpy(&q, &mid, 4);
+        if ((double)sqrtf(q) <= r) lo = mid; else hi = mid - 1u;
+    }
+    float q; memcpy(&q, &lo, 4);
+    return q;
+}
 
+}  // extern "C"
+
+// The search itself, device to device: d_xyt [3n] in, *d_off [n_alloc + 1] (exclusive row offsets, *d_off[n] = total)
+// and *d_vals out (cudaMalloc'ed here; the caller frees them).  Bounding box of the states from the host copy.
+int gmt_roadmap_build_csr_device(const float *states_xyt_host, const float *d_xyt, int n, int n_alloc, double disk_radius,
+                                 int **d_off_out, int **d_vals_out, int **d_counts_out, long long *total)
+{
     float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
     for (int i = 0; i < n; i++) {
-        const float x = states_xyt[3 * i], y = states_xyt[3 * i + 1];
+        const float x = states_xyt_host[3 * i], y = states_xyt_host[3 * i + 1];
         if (!(fabsf(x) < 1e30f) || !(fabsf(y) < 1e30f)) return GMT_ERR_INVALID;
         x0 = std::min(x0, x); y0 = std::min(y0, y); x1 = std::max(x1, x); y1 = std::max(y1, y);
     }
@@ -282,48 +324,91 @@ int gmt_build_neighbors(const float *states_xyt, int n, double disk_radius, int 
     const int ncell = g.nx * g.ny;
 
     const size_t N = (size_t)n;
-    float *d_xyt = nullptr; int *d_cell = nullptr, *d_start = nullptr, *d_fill = nullptr, *d_sums = nullptr;
-    int *d_row = nullptr, *d_vals = nullptr; float4 *d_sorted = nullptr; long long *d_total = nullptr;
+    int *d_cell = nullptr, *d_start = nullptr, *d_fill = nullptr, *d_sums = nullptr;
+    int *d_row = nullptr, *d_vals = nullptr, *d_counts = nullptr; float4 *d_sorted = nullptr; long long *d_total = nullptr;
     const int nbc = (ncell + SCAN_BLOCK - 1) / SCAN_BLOCK, nbr = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    RCK(cudaMalloc(&d_xyt, sizeof(float) * 3 * N));
-    RCK(cudaMalloc(&d_cell, sizeof(int) * N));
-    RCK(cudaMalloc(&d_start, sizeof(int) * ((size_t)ncell + 1)));
-    RCK(cudaMalloc(&d_fill, sizeof(int) * ((size_t)ncell + 1)));
-    RCK(cudaMalloc(&d_sums, sizeof(int) * (size_t)std::max(nbc, nbr)));
-    RCK(cudaMalloc(&d_row, sizeof(int) * (N + 1)));
-    RCK(cudaMalloc(&d_sorted, sizeof(float4) * N));
-    RCK(cudaMalloc(&d_total, sizeof(long long)));
-    RCK(cudaMemcpy(d_xyt, states_xyt, sizeof(float) * 3 * N, cudaMemcpyHostToDevice));
-    RCK(cudaMemset(d_start, 0, sizeof(int) * ((size_t)ncell + 1)));
+    auto release = [&](bool all) {
+        cudaFree(d_cell); cudaFree(d_start); cudaFree(d_fill); cudaFree(d_sums); cudaFree(d_sorted); cudaFree(d_total);
+        if (all) { cudaFree(d_row); cudaFree(d_vals); cudaFree(d_counts); }
+    };
+#define BCK(call)                                  \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) {                   \
+            fprintf(stderr, "gmt_roadmap: %s failed: %s\n", #call, cudaGetErrorString(e_)); \
+            release(true);                         \
+            return e_ == cudaErrorMemoryAllocation ? GMT_ERR_NOMEM : GMT_ERR_CUDA; \
+        }                                          \
+    } while (0)
+    BCK(cudaMalloc(&d_cell, sizeof(int) * N));
+    BCK(cudaMalloc(&d_start, sizeof(int) * ((size_t)ncell + 1)));
+    BCK(cudaMalloc(&d_fill, sizeof(int) * ((size_t)ncell + 1)));
+    BCK(cudaMalloc(&d_sums, sizeof(int) * (size_t)std::max(nbc, nbr)));
+    BCK(cudaMalloc(&d_row, sizeof(int) * ((size_t)std::max(n_alloc, n) + 1)));
+    BCK(cudaMalloc(&d_sorted, sizeof(float4) * N));
+    BCK(cudaMalloc(&d_total, sizeof(long long)));
+    BCK(cudaMemset(d_start, 0, sizeof(int) * ((size_t)ncell + 1)));
 
     const int tb = 256, gb = (n + tb - 1) / tb;
     cell_count_kernel<<<gb, tb>>>(d_xyt, n, g, d_cell, d_start);
     scan_block_kernel<<<nbc, SCAN_BLOCK>>>(d_start, ncell, d_sums);
     scan_sums_kernel<<<1, SCAN_BLOCK>>>(d_sums, nbc, d_total);
     scan_add_kernel<<<nbc, SCAN_BLOCK>>>(d_start, ncell, d_sums, d_total);
-    RCK(cudaMemcpy(d_fill, d_start, sizeof(int) * ((size_t)ncell + 1), cudaMemcpyDeviceToDevice));
+    BCK(cudaMemcpy(d_fill, d_start, sizeof(int) * ((size_t)ncell + 1), cudaMemcpyDeviceToDevice));
     cell_scatter_kernel<<<gb, tb>>>(d_xyt, n, d_cell, d_fill, d_sorted);
     const int gw = (n + NBR_WARPS - 1) / NBR_WARPS;
-    neighbour_kernel<0><<<gw, NBR_WARPS * 32>>>(n, g, disk_radius, d_start, d_sorted, d_row, nullptr);
-    RCK(cudaGetLastError());
-
-    int *h_counts = (int *)malloc(sizeof(int) * N);
-    if (!h_counts) return GMT_ERR_NOMEM;
-    RCK(cudaMemcpy(h_counts, d_row, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    const float qmax = q_threshold(disk_radius);
+    neighbour_kernel<0><<<gw, NBR_WARPS * 32>>>(n, g, qmax, d_start, d_sorted, d_row, nullptr);
+    BCK(cudaGetLastError());
+    if (d_counts_out) {                                        // row lengths, before the scan overwrites them
+        BCK(cudaMalloc(&d_counts, sizeof(int) * N));
+        BCK(cudaMemcpy(d_counts, d_row, sizeof(int) * N, cudaMemcpyDeviceToDevice));
+    }
     scan_block_kernel<<<nbr, SCAN_BLOCK>>>(d_row, n, d_sums);
     scan_sums_kernel<<<1, SCAN_BLOCK>>>(d_sums, nbr, d_total);
     scan_add_kernel<<<nbr, SCAN_BLOCK>>>(d_row, n, d_sums, d_total);
     long long tot = 0;
-    RCK(cudaMemcpy(&tot, d_total, sizeof(long long), cudaMemcpyDeviceToHost));
-    if (tot > 0x7fffffffLL) { free(h_counts); return GMT_ERR_INVALID; }
-    RCK(cudaMalloc(&d_vals, sizeof(int) * (size_t)std::max<long long>(tot, 1)));
-    neighbour_kernel<1><<<gw, NBR_WARPS * 32>>>(n, g, disk_radius, d_start, d_sorted, d_row, d_vals);
-    RCK(cudaGetLastError());
+    BCK(cudaMemcpy(&tot, d_total, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (tot > 0x7fffffffLL) { release(true); return GMT_ERR_INVALID; }
+    BCK(cudaMalloc(&d_vals, sizeof(int) * (size_t)std::max<long long>(tot, 1)));
+    neighbour_kernel<1><<<gw, NBR_WARPS * 32>>>(n, g, qmax, d_start, d_sorted, d_row, d_vals);
+    BCK(cudaGetLastError());
+    BCK(cudaDeviceSynchronize());
+#undef BCK
+    release(false);
+    *d_off_out = d_row; *d_vals_out = d_vals;
+    if (d_counts_out) *d_counts_out = d_counts;
+    if (total) *total = tot;
+    return GMT_OK;
+}
+
+extern "C" {
+
+int gmt_build_neighbors(const float *states_xyt, int n, double disk_radius, int device, int **vals, int **counts,
+                        long long *total)
+{
+    if (!states_xyt || n <= 0 || !vals || !counts || !(disk_radius >= 0.0)) return GMT_ERR_INVALID;
+    *vals = nullptr; *counts = nullptr;
+    if (total) *total = 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return GMT_ERR_CUDA;
+    RCK(cudaSetDevice(device));
+    const size_t N = (size_t)n;
+    float *d_xyt = nullptr;
+    RCK(cudaMalloc(&d_xyt, sizeof(float) * 3 * N));
+    if (cudaMemcpy(d_xyt, states_xyt, sizeof(float) * 3 * N, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d_xyt); return GMT_ERR_CUDA; }
+    int *d_off = nullptr, *d_vals = nullptr, *d_counts = nullptr;
+    long long tot = 0;
+    const int rc = gmt_roadmap_build_csr_device(states_xyt, d_xyt, n, n, disk_radius, &d_off, &d_vals, &d_counts, &tot);
+    cudaFree(d_xyt);
+    if (rc != GMT_OK) return rc;
+    int *h_counts = (int *)malloc(sizeof(int) * N);
     int *h_vals = (int *)malloc(sizeof(int) * (size_t)std::max<long long>(tot, 1));
-    if (!h_vals) { free(h_counts); return GMT_ERR_NOMEM; }
-    RCK(cudaMemcpy(h_vals, d_vals, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost));
-    cudaFree(d_xyt); cudaFree(d_cell); cudaFree(d_start); cudaFree(d_fill); cudaFree(d_sums);
-    cudaFree(d_row); cudaFree(d_vals); cudaFree(d_sorted); cudaFree(d_total);
+    bool ok = h_counts && h_vals &&
+              cudaMemcpy(h_counts, d_counts, sizeof(int) * N, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(h_vals, d_vals, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_off); cudaFree(d_vals); cudaFree(d_counts);
+    if (!ok) { free(h_counts); free(h_vals); return (h_counts && h_vals) ? GMT_ERR_CUDA : GMT_ERR_NOMEM; }
     *vals = h_vals; *counts = h_counts;
     if (total) *total = tot;
     return GMT_OK;

@@ -46,6 +46,34 @@ class GMT(object):
         self._handle = C.c_void_p()
         self._cpu_init(init_parameters, debug)
         self._gpu_init(debug, device)
+        self._common_init(words)
+
+    @classmethod
+    def from_states(cls, states, disk_radius=4 * math.sqrt(2), debug=False, device=0, words=4):
+        """Extension: a planner for the roadmap over `states` (float32[n, 3]) whose neighbour lists
+        -- the rule of CudaAgent.create_samples, cuda_agent.py:71-91, as gmt_build_neighbors states it -- are built
+        ON THE DEVICE and stay there (gmt_create_from_states): the lists never visit the host.  Same plans as
+        GMT({'states': states, 'neighbors': ..., 'num_neighbors': ...}) with the lists gmt_build_neighbors returns;
+        .neighbors / .num_neighbors download them on first use."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        self.states = np.ascontiguousarray(states, dtype=np.float32).reshape(-1, 3)
+        self.n = self.states.shape[0]
+        self.waypoints = np.arange(self.n).astype(np.int32)
+        self._neighbors = self._num_neighbors = None
+        self.cost = np.full(self.n, np.inf).astype(np.float32)
+        self.Vunexplored = np.full(self.n, 1).astype(np.int32)
+        self.Vopen = np.zeros_like(self.Vunexplored).astype(np.int32)
+        self.threadsPerBlock = 128
+        rc = self._lib.gmt_create_from_states(self.states.ctypes.data, self.n, float(disk_radius), int(device),
+                                              C.byref(self._handle))
+        _lib.check(rc, "gmt_create_from_states")
+        self._n_base = self.n
+        self._common_init(words)
+        return self
+
+    def _common_init(self, words):
         self.words = 4
         if words != 4:
             self.set_words(words)
@@ -62,8 +90,9 @@ class GMT(object):
         self.states = init_parameters['states']
         self.n = self.states.shape[0]
         self.waypoints = np.arange(self.n).astype(np.int32)
-        self.neighbors = init_parameters['neighbors']
-        self.num_neighbors = init_parameters['num_neighbors']
+        self._neighbors = init_parameters['neighbors']
+        self._num_neighbors = init_parameters['num_neighbors']
+        self._n_base = self.n
         # kept for callers that poke at them; the device owns the live copies
         self.cost = np.full(self.n, np.inf).astype(np.float32)
         self.Vunexplored = np.full(self.n, 1).astype(np.int32)
@@ -86,6 +115,35 @@ class GMT(object):
                                   cnt.ctypes.data, int(device), C.byref(self._handle))
         _lib.check(rc, "gmt_create")
 
+    def _download_neighbors(self):
+        total = C.c_longlong()
+        _lib.check(self._lib.gmt_get_neighbors(self._handle, None, None, 0, C.byref(total)), "gmt_get_neighbors")
+        counts = np.zeros(self._n_base, np.int32)
+        vals = np.zeros(max(total.value, 1), np.int32)
+        _lib.check(self._lib.gmt_get_neighbors(self._handle, counts.ctypes.data, vals.ctypes.data, int(vals.shape[0]),
+                                               C.byref(total)), "gmt_get_neighbors")
+        self._num_neighbors, self._neighbors = counts, vals[:total.value]
+
+    @property
+    def neighbors(self):
+        if self._neighbors is None:
+            self._download_neighbors()
+        return self._neighbors
+
+    @neighbors.setter
+    def neighbors(self, value):
+        self._neighbors = value
+
+    @property
+    def num_neighbors(self):
+        if self._num_neighbors is None:
+            self._download_neighbors()
+        return self._num_neighbors
+
+    @num_neighbors.setter
+    def num_neighbors(self, value):
+        self._num_neighbors = value
+
     def set_words(self, words):
         """Extension mode (not in the reference, which tries RSR, LSL, LSR, RSL: kernel.py:421-424):
         words=6 also tries the CCC words RLR and LRL in every later plan; words=4 restores parity mode."""
@@ -102,6 +160,37 @@ class GMT(object):
         obs = np.ascontiguousarray(obstacles, dtype=np.float32).reshape(-1, 4)
         m = obs.shape[0] if num_obs is None else int(np.asarray(num_obs).reshape(-1)[0])
         _lib.check(self._lib.gmt_set_obstacles(self._handle, obs.ctypes.data if m > 0 else None, m), "gmt_set_obstacles")
+
+    def set_obstacles_from_vehicles(self, vehicles, ego_xy, margin=2.5, max_dist=30.0, oriented=False):
+        """Extension: the reference's per-re-plan obstacle pipeline (cuda_agent.py:127-206: vehicle
+        boxes -> inflated boxes within 30 m of the ego) run ON THE DEVICE; the result becomes the resident obstacle
+        set, so ``run_step(dict(iter_parameters, obstacles=None))`` plans against it.  vehicles: rows [x, y, yaw_deg,
+        extent_x, extent_y, box_offset_x, box_offset_y] as synthetic_world.vehicles_to_obstacles takes them (the
+        NumPy statement of the same pipeline, which this reproduces bit for bit).  Returns the number of obstacles."""
+        v = np.asarray(vehicles, dtype=np.float64).reshape(-1, 7)
+        ego = np.asarray(ego_xy, dtype=np.float64).reshape(2)
+        yaw = np.radians(v[:, 2])
+        yaw32 = yaw.astype(np.float32)
+        rows = np.stack([v[:, 0], v[:, 1], np.cos(yaw), np.sin(yaw), v[:, 3], v[:, 4], v[:, 5], v[:, 6],
+                         np.array([math.cos(a) for a in yaw32], np.float64),
+                         np.array([math.sin(a) for a in yaw32], np.float64)], 1) if len(v) else np.zeros((0, 10))
+        rows = np.ascontiguousarray(rows, np.float64)
+        m = C.c_int()
+        rc = self._lib.gmt_set_obstacles_from_vehicles(self._handle, rows.ctypes.data if len(v) else None, len(v),
+                                                       float(ego[0]), float(ego[1]), float(margin), float(max_dist),
+                                                       1 if oriented else 0, C.byref(m))
+        _lib.check(rc, "gmt_set_obstacles_from_vehicles")
+        return m.value
+
+    def get_obstacles(self):
+        """The resident obstacle set: (corner boxes float32[m, 4], oriented records float32[m, 6] or None)."""
+        m = C.c_int()
+        _lib.check(self._lib.gmt_get_obstacles(self._handle, None, None, 0, C.byref(m)), "gmt_get_obstacles")
+        xyxy = np.zeros((max(m.value, 1), 4), np.float32)
+        obb = np.zeros((max(m.value, 1), 6), np.float32)
+        _lib.check(self._lib.gmt_get_obstacles(self._handle, xyxy.ctypes.data, obb.ctypes.data, m.value, C.byref(m)),
+                   "gmt_get_obstacles")
+        return xyxy[:m.value], (obb[:m.value] if obb[:m.value].any() else None)
 
     def update_obstacles(self, index, obstacles):
         """Replace the boxes `index` of the resident set in place (only those cross PCIe)."""
@@ -129,7 +218,7 @@ class GMT(object):
     def reset_inserted(self):
         """Drops every state appended by insert_states."""
         _lib.check(self._lib.gmt_reset_inserted(self._handle), "gmt_reset_inserted")
-        self.n = int(np.asarray(self.num_neighbors).shape[0])
+        self.n = int(self._n_base)
         self.states = np.asarray(self.states).reshape(-1, 3)[:self.n]
         self.waypoints = np.arange(self.n).astype(np.int32)
         self._parent = self._cost = None

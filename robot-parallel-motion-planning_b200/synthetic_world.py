@@ -118,8 +118,10 @@ def nearest_state(states, x, y):
 
 
 def make_world(config=None, n=None, m=None, mode=None, layout=None, seed=None, sampler=None,
-               neighbor_builder=None, radius=2.0, threshold=1.0, side=None):
-    """Returns (init_parameters, iter_parameters, meta) for a BASELINE config or explicit sizes."""
+               neighbor_builder=None, radius=2.0, threshold=1.0, side=None, with_neighbors=True):
+    """Returns (init_parameters, iter_parameters, meta) for a BASELINE config or explicit sizes.
+    with_neighbors=False leaves the lists out (init_parameters['neighbors'] = None) for GMT.from_states, which
+    builds them on the device."""
     cfg = dict(CONFIGS[config]) if config is not None else {}
     n = int(n if n is not None else cfg["n"])
     m = int(m if m is not None else cfg["m"])
@@ -132,7 +134,7 @@ def make_world(config=None, n=None, m=None, mode=None, layout=None, seed=None, s
 
     states = np.ascontiguousarray(sampler(seed, n, side, mode), np.float32)
     n = states.shape[0]
-    neighbors, num_neighbors = neighbor_builder(states, DISK_RADIUS)
+    neighbors, num_neighbors = neighbor_builder(states, DISK_RADIUS) if with_neighbors else (None, None)
     rng = np.random.default_rng(seed)
     obstacles, num_obs = make_obstacles(rng, m, side, layout)
     start = nearest_clear_state(states, 0.1 * side, 0.1 * side, obstacles, m)
@@ -143,7 +145,7 @@ def make_world(config=None, n=None, m=None, mode=None, layout=None, seed=None, s
     iter_parameters = {'start': start, 'goal': goal, 'radius': radius, 'threshold': threshold,
                        'obstacles': obstacles, 'num_obs': num_obs}
     meta = dict(n=n, m=m, side=side, seed=seed, mode=mode, layout=layout,
-                mean_degree=float(num_neighbors.mean()) if n else 0.0)
+                mean_degree=float(num_neighbors.mean()) if (n and num_neighbors is not None) else None)
     return init_parameters, iter_parameters, meta
 
 

@@ -753,3 +753,91 @@ def test_obstacle_deltas_on_the_resident_set(GMT):
     assert not np.array_equal(g.parent, parent0)                                       # (and the tree did change)
     with pytest.raises(_lib.GmtError):
         g.update_obstacles([20], new[:1])                                              # index out of range
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: device-side ingestion, device-built roadmap, resident query lists
+# ------------------------------------------------------------------------------------------------
+def test_device_obstacle_ingestion_equals_the_host_pipeline(GMT):
+    """gmt_set_obstacles_from_vehicles (vehicle boxes -> obstacle set on the device) against
+    synthetic_world.vehicles_to_obstacles, the NumPy statement of cuda_agent.py:127-206: the resident array is the
+    host array BIT FOR BIT (corner boxes; oriented records + their enlarged bounding boxes), and plans agree."""
+    import synthetic_world as sw
+    init, it, meta = _world(None, 2500, 0, 71)
+    rng = np.random.default_rng(9)
+    k = 1500                                            # more than one 1024-thread chunk: ordered compaction across chunks
+    st = init['states']
+    ego = (float(st[it['start'], 0]), float(st[it['start'], 1]))
+    veh = np.stack([rng.uniform(ego[0] - 45, ego[0] + 45, k), rng.uniform(ego[1] - 45, ego[1] + 45, k),
+                    rng.uniform(-180, 180, k), rng.uniform(0.4, 1.5, k), rng.uniform(0.3, 0.8, k),
+                    rng.uniform(-0.3, 0.3, k), rng.uniform(-0.1, 0.1, k)], 1)
+    veh[7] = [ego[0], ego[1], 10.0, 1.0, 0.5, 0.0, 0.0]   # the ego itself: distance 0, dropped
+    g = GMT(init)
+    obs, num = sw.vehicles_to_obstacles(veh, ego, margin=0.2)
+    m = g.set_obstacles_from_vehicles(veh, ego, margin=0.2)
+    dev, _ = g.get_obstacles()
+    assert m == int(num[0]) and 0 < m < k
+    assert np.array_equal(dev.view(np.uint32), obs.view(np.uint32))
+    route_dev = list(g.run_step(dict(it, obstacles=None), iter_limit=300))
+    parent_dev = g.parent.copy()
+    h = GMT(init)
+    route_host = list(h.run_step(dict(it, obstacles=obs, num_obs=num), iter_limit=300))
+    assert route_dev == route_host and np.array_equal(parent_dev, h.parent)
+    # oriented form (extension mode)
+    from gmt_planner import oriented_records
+    rect, num = sw.vehicles_to_obstacles(veh, ego, margin=0.2, oriented=True)
+    m = g.set_obstacles_from_vehicles(veh, ego, margin=0.2, oriented=True)
+    box_dev, rec_dev = g.get_obstacles()
+    assert m == int(num[0])
+    assert np.array_equal(rec_dev.view(np.uint32), oriented_records(rect).view(np.uint32))
+    h.run_step(dict(it, obstacles=rect, num_obs=num, obstacle_format='oriented'), iter_limit=300)
+    box_host, _ = h.get_obstacles()
+    assert np.array_equal(box_dev.view(np.uint32), box_host.view(np.uint32))
+    g.run_step(dict(it, obstacles=None), iter_limit=300)
+    assert np.array_equal(g.parent, h.parent) and list(g.route) == list(h.route)
+    # nothing near: empty set
+    assert g.set_obstacles_from_vehicles(veh[:5] + 1e4, ego) == 0
+    report("device obstacle ingestion: %d vehicles -> %d obstacles, array and plan identical to the host pipeline "
+           "(corner and oriented form)" % (k, m))
+
+
+def test_roadmap_built_on_the_device_equals_the_host_lists(GMT, gmt_lib):
+    """GMT.from_states (gmt_create_from_states: neighbour lists built and kept on the device) gives the plan of
+    GMT(init) and, downloaded, the lists of gmt_build_neighbors (which equal oracle/world_oracle.py, tested above)."""
+    init, it, meta = _world(None, 30000, 60, 13)
+    a = GMT(init)
+    b = GMT.from_states(init['states'])
+    assert np.array_equal(b.num_neighbors, init['num_neighbors']) and np.array_equal(b.neighbors, init['neighbors'])
+    ra = list(a.run_step(it, iter_limit=300))
+    rb = list(b.run_step(it, iter_limit=300))
+    assert ra == rb and (a.status, a.iterations) == (b.status, b.iterations)
+    assert np.array_equal(a.parent, b.parent) and np.array_equal(a.dev_cost.view(np.uint32), b.dev_cost.view(np.uint32))
+    # rows longer than 64 entries take the shared-memory sort: a denser map
+    import synthetic_world as sw
+    from oracle.world_oracle import build_neighbors
+    st = sw.cuda_sampler(3, 6000, 60.0)
+    nb, num = sw.cuda_neighbor_builder(st, sw.DISK_RADIUS)
+    onb, onum = build_neighbors(st, sw.DISK_RADIUS)
+    assert num.max() > 64 and np.array_equal(num, onum) and np.array_equal(nb, onb)
+
+
+def test_resident_query_list_equals_the_host_batch(GMT, gmt_lib):
+    """gmt_set_queries + gmt_plan_queries (what bench.py times as `value`) == gmt_plan_batch."""
+    import _lib
+    import synthetic_world as sw
+    init, it, meta = _world(None, 4000, 40, 29)
+    g = GMT(init)
+    g.set_obstacles(it['obstacles'], it['num_obs'])
+    starts, goals = sw.make_reachable_queries(g, meta["n"], 200, 5)
+    res, routes = sw.plan_batch(g, starts, goals, route_stride=64)
+    _lib.check(gmt_lib.gmt_set_queries(g._handle, starts.ctypes.data, goals.ctypes.data, len(starts)), "gmt_set_queries")
+    res2 = (_lib.GmtResult * len(starts))()
+    routes2 = np.zeros((len(starts), 64), np.int32)
+    for _ in range(2):
+        _lib.check(gmt_lib.gmt_plan_queries(g._handle, 2.0, 1.0, 1000, res2, routes2.ctypes.data, 64), "gmt_plan_queries")
+        assert np.array_equal(routes, routes2)
+        assert all((a.status, a.iterations, a.route_len) == (b.status, b.iterations, b.route_len) for a, b in zip(res, res2))
+    be = (C.c_ulonglong * (2 * len(starts)))()
+    teams = C.c_int()
+    _lib.check(gmt_lib.gmt_debug_batch_times(g._handle, be, len(starts), C.byref(teams)), "gmt_debug_batch_times")
+    assert teams.value >= 1 and all(be[2 * i + 1] >= be[2 * i] for i in range(len(starts)))
