@@ -64,6 +64,7 @@ WORKLOADS = {
     "cfg5": "cfg5: single query on ONE 1M-sample roadmap (2k obstacles), edge evaluation sharded by node range over "
             "the GPUs, per-wavefront exchange of the packed cost/parent keys over NVLink",
 }
+PHASES = ("frontier", "select", "connect", "exchange", "exchange_push", "exchange_grid_barrier", "exchange_wait_for_peers")
 SINGLE_CONFIG = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg5": 5}
 
 
@@ -556,7 +557,7 @@ def time_sharded(ctx, K=8):
     same = int(list(out["route"]) == single)
     dbg = (C.c_ulonglong * 8)()
     lib.gmt_debug_counters(g._handle, dbg)
-    phases = [dbg[0] / 1e3, dbg[1] / 1e3, dbg[4] / 1e3, dbg[2] / 1e3]
+    phases = [dbg[0] / 1e3, dbg[1] / 1e3, dbg[4] / 1e3, dbg[2] / 1e3, dbg[5] / 1e3, dbg[6] / 1e3, dbg[7] / 1e3]
     nccl_ms = 0.0
     if world > 1:
         multi_gpu.close_peers(g)
@@ -586,8 +587,8 @@ def time_sharded(ctx, K=8):
                     "route_len": len(single), "pairs_evaluated": res1.edge_evals, "words_swept": res1.word_checks},
            "identical_tree_on_every_rank": bool(flags.item()),
            "nccl_allreduce_min_form_ms": nccl_ms if world > 1 else None,
-           "phase_us_per_wavefront_max_over_ranks": dict(zip(("frontier", "select", "connect", "exchange"), (ph_max / wf).tolist())),
-           "phase_us_per_wavefront_min_over_ranks": dict(zip(("frontier", "select", "connect", "exchange"), (ph_min / wf).tolist())),
+           "phase_us_per_wavefront_max_over_ranks": dict(zip(PHASES, (ph_max / wf).tolist())),
+           "phase_us_per_wavefront_min_over_ranks": dict(zip(PHASES, (ph_min / wf).tolist())),
            "algorithmic_tflops": res1.edge_pairs * f_edge(m) / (t_dev / K) * 1e-12}
     # bytes a GPU sends per wavefront: 8 B per candidate node it connected, to each of world-1 peers
     reached = int(np.sum(np.isfinite(g.dev_cost))) if world > 1 else None
