@@ -776,7 +776,7 @@ def run_b200(args):
         "gpu_launches": acc["launches"] + e2e_launch["n"],
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"]},
-        "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel<4,false,512> (team mode)", "achieved": achieved,
+        "roofline": {"bound": "fp32", "kernel": "gmt_plan_kernel<%d,false,1024> (batch: one team of 32 warps per SM)" % args.words, "achieved": achieved,
                      "peak": fp32_peak.value, "unit": "TFLOP/s", "frac": achieved / fp32_peak.value if fp32_peak.value else None,
                      "executed": executed, "executed_frac": executed / fp32_peak.value if fp32_peak.value else None,
                      "traffic": (ncu.get("gmt_plan_kernel_batch") or {}).get("dram_bytes_per_launch"),

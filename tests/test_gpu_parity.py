@@ -841,3 +841,30 @@ def test_resident_query_list_equals_the_host_batch(GMT, gmt_lib):
     teams = C.c_int()
     _lib.check(gmt_lib.gmt_debug_batch_times(g._handle, be, len(starts), C.byref(teams)), "gmt_debug_batch_times")
     assert teams.value >= 1 and all(be[2 * i + 1] >= be[2 * i] for i in range(len(starts)))
+
+
+def test_batch_launch_shapes_give_the_same_plans(GMT, gmt_lib):
+    """A batch is the same set of plans whatever the launch shape: 1024-thread blocks in teams of one SM (default),
+    512-thread blocks in teams of two, larger teams, hand-out order by distance or by measured durations, and a list
+    shorter than the number of teams (teams grow)."""
+    import synthetic_world as sw
+    init, it, meta = _world(None, 4000, 40, 31)
+    g = GMT(init)
+    g.set_obstacles(it['obstacles'], it['num_obs'])
+    starts, goals = sw.make_reachable_queries(g, meta["n"], 300, 7)
+    res0, routes0 = sw.plan_batch(g, starts, goals, route_stride=64)
+    key0 = [(r.status, r.iterations, r.route_len, np.float32(r.goal_cost).view(np.uint32)) for r in res0]
+    assert sum(r.status == 0 for r in res0) > 100
+    shapes = [{"batch_block": 512}, {"batch_block": 512, "team_blocks": 4}, {"batch_block": 1024, "team_blocks": 2},
+              {"batch_block": 1024, "team_blocks": 1, "order_by_history": 0}, {"order_by_history": 1, "team_blocks": -1}]
+    for opts in shapes:
+        for k, v in opts.items():
+            g.set_option(k, v)
+        for _ in range(2):                                   # second pass: the order comes from the measured durations
+            res, routes = sw.plan_batch(g, starts, goals, route_stride=64)
+            assert np.array_equal(routes, routes0), opts
+            assert [(r.status, r.iterations, r.route_len, np.float32(r.goal_cost).view(np.uint32)) for r in res] == key0, opts
+    res, routes = sw.plan_batch(g, starts[:20], goals[:20], route_stride=64)      # 20 queries on 148 SMs: teams of 4
+    assert np.array_equal(routes, routes0[:20])
+    assert [(r.status, r.iterations, r.route_len) for r in res] == [k[:3] for k in key0[:20]]
+    report("batch launch shapes (512 / 1024 threads, teams of 1 / 2 / 4 SMs, both hand-out orders, short list): 300 plans identical")
