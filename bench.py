@@ -412,7 +412,8 @@ class Ctx:
                 wall += time.perf_counter() - t0
                 ev[k][1].record(self.stream)
             self.stream.synchronize()
-        return sum(a.elapsed_time(b) for a, b in ev) * 1e-3, wall
+        self.last_steps_ms = [a.elapsed_time(b) for a, b in ev]
+        return sum(self.last_steps_ms) * 1e-3, wall
 
 
 def time_single(ctx, name, K=30, words=4, oriented=False):
@@ -506,6 +507,7 @@ def gpu_reference_leg(ctx, g, init, it, tag, budget_s=20.0):
 
 
 def time_sharded(ctx, K=8):
+    K = int(os.environ.get("GMT_BENCH_CFG5_STEPS", K))
     """cfg5: ONE plan on the 1M-sample roadmap.  N = 1: the plain persistent plan.  N > 1: node-range sharding,
     fused form (one launch per GPU, per-wavefront exchange over NVLink peer memory inside the kernel) timed with
     CUDA events, max over ranks; the NCCL all-reduce(min) form once beside it; every rank's route must be the
@@ -550,11 +552,21 @@ def time_sharded(ctx, K=8):
         out["route"], out["res"] = step()
     ctx.barrier()
 
+    kern_steps = []
+
     def timed_step():
         out["route"], out["res"] = step()
+        kern_steps.append(round(out["res"].device_ms, 3))
     t_dev, wall = ctx.timed(K, timed_step, pre=(lambda k: ctx.barrier()) if world > 1 else None)
+    steps_ms = [round(v, 3) for v in ctx.last_steps_ms]
+    kernel_ms_last = out["res"].device_ms
+    if world > 1:
+        allk = [None] * world
+        ctx.dist.all_gather_object(allk, kern_steps)
+        kern_steps = allk
     ctx.barrier()
     same = int(list(out["route"]) == single)
+    same_fused = same
     dbg = (C.c_ulonglong * 8)()
     lib.gmt_debug_counters(g._handle, dbg)
     phases = [dbg[0] / 1e3, dbg[1] / 1e3, dbg[4] / 1e3, dbg[2] / 1e3, dbg[5] / 1e3, dbg[6] / 1e3, dbg[7] / 1e3]
@@ -569,7 +581,7 @@ def time_sharded(ctx, K=8):
             nccl_ms = (time.perf_counter() - t0) * 1e3
         same = int(same and list(r2) == single)
     t_dev, wall, nccl_ms, single_ms = multi_gpu.max_over_ranks([t_dev, wall, nccl_ms, single_ms], device=ctx.dev)
-    flags = torch.tensor([same], device=ctx.dev)
+    flags = torch.tensor([same, same_fused], device=ctx.dev)
     ph = torch.tensor(phases, dtype=torch.float64, device=ctx.dev)
     ph_max, ph_min = ph.clone(), ph.clone()
     if ctx.dist is not None:
@@ -579,13 +591,14 @@ def time_sharded(ctx, K=8):
     wf = max(res1.iterations, 1)
     rec = {"workload": WORKLOADS["cfg5"], "n": n, "m": m, "seed": meta["seed"], "n_gpus": world, "steps": K,
            "ms_per_plan": t_dev / K * 1e3, "e2e_ms_per_plan": wall / K * 1e3, "plans_per_s": K / t_dev,
+           "steps_ms_rank0": steps_ms, "kernel_ms_last_plan_rank0": kernel_ms_last, "kernel_ms_steps_by_rank": kern_steps,
            "roadmap_build_ms": create_ms, "single_gpu_ms": single_ms, "speedup_vs_single_gpu": single_ms / (t_dev / K * 1e3),
            "exchange": "none (one GPU)" if world == 1 else
                        "in-kernel stores into the peers' inboxes over NVLink + per-block arrival counters in peer memory",
            "nvlink_bytes_per_wavefront_per_gpu": None,
            "plan": {"status": res1.status, "wavefronts": res1.iterations, "edge_checks": res1.edge_pairs,
                     "route_len": len(single), "pairs_evaluated": res1.edge_evals, "words_swept": res1.word_checks},
-           "identical_tree_on_every_rank": bool(flags.item()),
+           "identical_tree_on_every_rank": bool(flags[0].item()), "fused_form_identical": bool(flags[1].item()),
            "nccl_allreduce_min_form_ms": nccl_ms if world > 1 else None,
            "phase_us_per_wavefront_max_over_ranks": dict(zip(PHASES, (ph_max / wf).tolist())),
            "phase_us_per_wavefront_min_over_ranks": dict(zip(PHASES, (ph_min / wf).tolist())),
