@@ -436,6 +436,9 @@ def time_single(ctx, name, K=30, words=4, oriented=False):
         lo, hi = np.minimum(obs[:, :2], obs[:, 2:]), np.maximum(obs[:, :2], obs[:, 2:])
         rect = np.concatenate([(lo + hi) / 2, (hi - lo) / 2, rng.uniform(-np.pi, np.pi, (len(obs), 1))], 1).astype(np.float32)
         it = dict(it, obstacles=rect, obstacle_format='oriented')
+        g.run_step(dict(it, goal=-1), iter_limit=1000)           # the turned rectangles change what is reachable:
+        goal = int(g.last_result.farthest_frontier)              # plan to the farthest state the wavefront enters
+        it = dict(it, goal=goal)
         g.run_step(it, iter_limit=1000)
     else:
         _lib.check(lib.gmt_set_obstacles(g._handle, obs.ctypes.data if m else None, m), "gmt_set_obstacles")

@@ -3,12 +3,20 @@ import sys, ctypes as C, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'robot-parallel-motion-planning_b200')
 import _lib, synthetic_world as sw
 from gmt_planner import GMT
-if sys.argv[1] == '0':
-    init, it, meta = sw.make_world(n=int(sys.argv[2]), m=int(sys.argv[3]), seed=23)
+if sys.argv[1].startswith('cfg'):                 # a bench workload by name
+    import bench
+    init, it, meta = bench.make_named_world(sys.argv[1])
+    g = GMT(init)
+    for a in sys.argv[2:]:
+        g.set_option(a.split('=')[0], int(a.split('=')[1]))
+    it, _c = bench.bench_query(sys.argv[1], init, it, meta)
 else:
-    init, it, meta = sw.make_world(int(sys.argv[1]))
-it = dict(it, goal=sw.pick_reachable_goal(init, it, meta["side"]))
-g = GMT(init)
+    if sys.argv[1] == '0':
+        init, it, meta = sw.make_world(n=int(sys.argv[2]), m=int(sys.argv[3]), seed=23)
+    else:
+        init, it, meta = sw.make_world(int(sys.argv[1]))
+    it = dict(it, goal=sw.pick_reachable_goal(init, it, meta["side"]))
+    g = GMT(init)
 for rep in range(2):
     g.run_step(it, iter_limit=1000)
 res = g.last_result

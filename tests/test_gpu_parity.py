@@ -565,6 +565,14 @@ def test_fused_sharded_plan_on_two_gpus():
     out = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280).stdout
     assert "identical tree on every rank: True (NCCL path: True)" in out, out[-2000:]
     report("2 GPUs, 30k nodes: " + [l for l in out.splitlines() if "fused peer-memory" in l][0].strip())
+    # the same on a 300k-node map, 12 fused plans in a row, EVERY tree compared: with fronts this large the block that
+    # pushes wavefront k's keys still works while the others expand wavefront k + 1 (a race there showed up as an
+    # occasional diverging tree in round 2, which one plan per run did not catch)
+    cmd = cmd[:-3] + [os.path.join(root, "scripts", "sharded_repeat.py"), "300000", "1000", "12", "1"]
+    cmd[cmd.index("29533")] = "29534"
+    out = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280).stdout
+    assert "every tree identical on every rank: True" in out and "MISMATCH" not in out, out[-2000:]
+    report("2 GPUs, 300k nodes: " + [l for l in out.splitlines() if "every tree identical" in l][0].strip())
 
 
 def test_appended_states_equal_the_rebuilt_roadmap(GMT, oracles):
