@@ -34,6 +34,7 @@ for name in names:
     lib.gmt_debug_counters(g._handle, d)
     w = max(r.iterations, 1)
     print("%-6s %9.3f ms (min of 8; median %.3f); %d wavefronts, pairs evaluated %d, words swept %d; per wavefront us: frontier %.1f "
-          "select %.1f connect %.1f" % (name, min(ms[2:]), float(np.median(ms[2:])), r.iterations, r.edge_evals, r.word_checks,
-                                        d[0] / 1e3 / w, d[1] / 1e3 / w, d[4] / 1e3 / w), flush=True)
+          "select %.1f connect %.1f (fused step: list+keys in after %.1f, rows after %.1f)"
+          % (name, min(ms[2:]), float(np.median(ms[2:])), r.iterations, r.edge_evals, r.word_checks,
+             d[0] / 1e3 / w, d[1] / 1e3 / w, d[4] / 1e3 / w, d[5] / 1e3 / w, d[6] / 1e3 / w), flush=True)
     del g

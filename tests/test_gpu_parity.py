@@ -876,3 +876,32 @@ def test_batch_launch_shapes_give_the_same_plans(GMT, gmt_lib):
     assert np.array_equal(routes, routes0[:20])
     assert [(r.status, r.iterations, r.route_len) for r in res] == [k[:3] for k in key0[:20]]
     report("batch launch shapes (512 / 1024 threads, teams of 1 / 2 / 4 SMs, both hand-out orders, short list): 300 plans identical")
+
+
+def test_fused_frontier_step_equals_the_classic_phases(GMT, gmt_lib):
+    """Single plans on small fronts take the frontier step that every block replicates from the staged open list (no
+    grid-wide expansion phase, next open list staged while the wavefront connects); option fused_frontier = 0 keeps
+    the three classic phases.  Same tree bit for bit, same exits (goal, limit, dead tails), on maps whose fronts stay
+    under / cross / exceed the limits of the fused form."""
+    cases = [(2500, 25, 41, "uniform"), (12000, 120, 42, "uniform"), (40000, 300, 43, "uniform"), (6000, 0, 44, "uniform"),
+             (9000, 400, 45, "uniform")]
+    total = 0
+    for n, m, seed, layout in cases:
+        init, it, meta = _world(None, n, m, seed, layout=layout)
+        g0, g1 = GMT(init), GMT(init)
+        g0.set_option("fused_frontier", 0)
+        g1.set_option("fused_frontier", 1)
+        rng = np.random.default_rng(seed)
+        goals = [int(it['goal']), -1] + [int(v) for v in rng.integers(0, n, 4)]
+        for goal in goals:
+            for limit in (1000, 7):
+                q = dict(it, goal=goal)
+                r0 = list(g0.run_step(q, iter_limit=limit))
+                r1 = list(g1.run_step(q, iter_limit=limit))
+                assert (g0.status, g0.iterations) == (g1.status, g1.iterations), (n, goal, limit)
+                assert r0 == r1, (n, goal, limit)
+                assert np.array_equal(g0.parent, g1.parent), (n, goal, limit)
+                assert np.array_equal(g0.dev_cost.view(np.uint32), g1.dev_cost.view(np.uint32)), (n, goal, limit)
+                assert g0.last_result.edge_pairs == g1.last_result.edge_pairs, (n, goal, limit)
+                total += 1
+    report("fused frontier step vs classic phases: %d plans on 5 maps, trees / exits / edge-check counts identical" % total)
