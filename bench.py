@@ -539,9 +539,12 @@ def time_sharded(ctx, K=8):
     create_ms = (time.perf_counter() - t0) * 1e3
     ctx.bind(g)
     with torch.cuda.stream(ctx.stream):
-        single = list(g.run_step(it, iter_limit=1000))                   # also the check value for the sharded forms
+        single_ms = 1e30
+        for _ in range(4 if world > 1 else 1):                           # warm (N = 1 times this plan below anyway)
+            single = list(g.run_step(it, iter_limit=1000))               # also the check value for the sharded forms
+            if _ > 0 or world == 1:
+                single_ms = min(single_ms, g.last_result.device_ms)
     res1 = g.last_result
-    single_ms = res1.device_ms
     if world > 1:
         multi_gpu.open_peers(g, rank, world)
 
@@ -621,6 +624,9 @@ def time_sharded(ctx, K=8):
 
 def run_b200(args):
     import ctypes as C
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":        # (its banner goes to stdout, in front of the JSON line)
+        os.environ["NCCL_DEBUG"] = "WARN"
+
     import multi_gpu
     import synthetic_world as sw
     from gmt_planner import GMT

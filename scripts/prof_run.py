@@ -1,5 +1,5 @@
 """Profiling target (run under ncu through gpurun): a few launches of ONE kernel on a bench workload, nothing else.
-usage: prof_run.py batch [queries] | cfg2 | cfg3u | cfg5 | words6 | oriented"""
+usage: prof_run.py batch [queries] | cfg2 | cfg3u | cfg5 | words6 | oriented | edge"""
 import sys
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'robot-parallel-motion-planning_b200')
@@ -15,6 +15,20 @@ if mode == "batch":
     for rep in range(3):
         res, _r = sw.plan_batch(g, starts[:q], goals[:q])
     print("batch of %d: %.2f ms -> %.0f plans/s" % (q, res[0].device_ms, q / res[0].device_ms * 1e3))
+elif mode == "edge":                    # the kernel-level entry on 2^18 neighbour pairs of the cfg4 map (bench.py's edge_kernel)
+    import ctypes as C, _lib
+    init, it, meta = bench.make_named_world("cfg4")
+    g = GMT(init)
+    g.set_obstacles(it['obstacles'], it['num_obs'])
+    rng = np.random.default_rng(7)
+    nbr, num = init['neighbors'], init['num_neighbors']
+    rows = np.repeat(np.arange(meta["n"], dtype=np.int32), num)
+    sel = rng.integers(0, len(nbr), 1 << 18)
+    ey, ex = np.ascontiguousarray(rows[sel]), np.ascontiguousarray(nbr[sel].astype(np.int32))
+    ms = C.c_float()
+    for rep in range(3):
+        _lib.check(g._lib.gmt_edge_costs(g._handle, ey.ctypes.data, ex.ctypes.data, 1 << 18, 2.0, None, None, None, C.byref(ms)), "edge")
+    print("edge kernel: %.3f ms for %d pairs -> %.0f M edge checks/s" % (ms.value, 1 << 18, (1 << 18) / ms.value * 1e-3))
 else:
     name = {"words6": "cfg2", "oriented": "cfg2"}.get(mode, mode)
     init, it, meta = bench.make_named_world(name)
