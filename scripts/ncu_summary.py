@@ -1,5 +1,5 @@
 """Development aid: the handful of ncu metrics bench.py quotes (profiles/ncu_summary.json) from .ncu-rep captures.
-usage: ncu_summary.py name=report.ncu-rep ...   (prints JSON; run where ncu is installed, no GPU needed)"""
+usage: ncu_summary.py name=report.ncu-rep[:launch] ...   (prints JSON; run where ncu is installed, no GPU needed)"""
 import csv, io, json, subprocess, sys
 KEYS = {"gpu__time_duration.sum": "duration", "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "fma_pipe_pct",
@@ -15,9 +15,13 @@ UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-3, "ms":
 out = {}
 for arg in sys.argv[1:]:
     name, rep = arg.split("=")
+    idx = 0
+    if rep.rsplit(":", 1)[-1].isdigit():                     # report.ncu-rep:K = the K-th profiled launch of the report
+        rep, k = rep.rsplit(":", 1)
+        idx = int(k)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + idx]
     rec = {"kernel": vals[hdr.index("Kernel Name")], "report": rep.split("/")[-1]}
     for k, nm in KEYS.items():
         if k in hdr:
