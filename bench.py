@@ -624,8 +624,8 @@ def time_sharded(ctx, K=8):
 
 def run_b200(args):
     import ctypes as C
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":        # (its banner goes to stdout, in front of the JSON line)
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):   # NCCL printf()s its version banner to stdout at these
+        os.environ.pop("NCCL_DEBUG")                                      # levels, in front of the JSON line
 
     import multi_gpu
     import synthetic_world as sw
