@@ -601,7 +601,7 @@ def time_sharded(ctx, K=8):
            "steps_ms_rank0": steps_ms, "kernel_ms_last_plan_rank0": kernel_ms_last, "kernel_ms_steps_by_rank": kern_steps,
            "roadmap_build_ms": create_ms, "single_gpu_ms": single_ms, "speedup_vs_single_gpu": single_ms / (t_dev / K * 1e3),
            "exchange": "none (one GPU)" if world == 1 else
-                       "in-kernel: one block stores this GPU's final keys into the peers' inboxes over NVLink and publishes a flag per peer (release); every block waits for the peers' flags by itself (acquire)",
+                       "in-kernel: one block stores this GPU's final keys into the peers' inboxes over NVLink and publishes a flag per peer (one release fence); a warp of the next frontier phase waits for the flag of the GPU that owns the node it expands, not for all peers",
            "nvlink_bytes_per_wavefront_per_gpu": None,
            "plan": {"status": res1.status, "wavefronts": res1.iterations, "edge_checks": res1.edge_pairs,
                     "route_len": len(single), "pairs_evaluated": res1.edge_evals, "words_swept": res1.word_checks},
