@@ -765,6 +765,18 @@ def run_b200(args):
                 del keep
             except Exception as e:          # a sub-record must never take the headline down
                 sub[name] = {"failed": repr(e)}
+        if args.words == 4 and not args.oriented:
+            # extension mode (north star: six words, oriented rectangles; not in the reference -- parity unpinned,
+            # DESIGN 7b) on the cfg2 map, so that the default line carries a number for it
+            for tag, kw in (("cfg2_six_words", {"words": 6}), ("cfg2_oriented_rectangles", {"oriented": True})):
+                try:
+                    rec, keep = time_single(ctx, "cfg2", K=20, **kw)
+                    rec["extension_mode"] = "parity unpinned: defined by oracle/gmt_oracle.c, checked against it in tests/test_gpu_extensions.py"
+                    rec["ncu"] = profile_json("ncu_summary.json").get("gmt_plan_kernel_words6" if "words" in kw else "gmt_plan_kernel_oriented")
+                    sub[tag] = rec
+                    del keep
+                except Exception as e:
+                    sub[tag] = {"failed": repr(e)}
     if not args.no_sub:
         try:
             sub["cfg5"] = time_sharded(ctx)
